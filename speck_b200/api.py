@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in include/speck_b200.h.
+
+Mirrors the reference's host-side objects for the hot path:
+    Context      <-> spECK::spECKConfig            (include/spECKConfig.h:8-53)
+    DeviceCSR    <-> dCSR<T>                       (include/dCSR.h:9-22), convert() up/down
+    Context.multiply(A, B, C) <-> spECK::MultiplyspECK<T,4,1024,...>(A, B, C, config, timings)
+                                                   (include/Multiply.h:15-16)
+    Context.compare(ref, cmp) <-> spECK::Compare   (include/Compare.h:5-6)
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is visible, every
+entry point raises SpeckError.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .matrices import HostCSR
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libspeck_b200.so")
+
+NUM_CLASSES = 12
+BIN_NAMES = ["direct", "sort4", "sort8", "sort16", "sort32", "sort64", "sort128", "sort256",
+             "sort512", "sort1024", "dense"]
+
+
+class SpeckError(RuntimeError):
+    pass
+
+
+class CsrStruct(ctypes.Structure):
+    _fields_ = [("rows", ctypes.c_size_t), ("cols", ctypes.c_size_t), ("nnz", ctypes.c_size_t),
+                ("data", ctypes.c_void_p), ("row_offsets", ctypes.c_void_p),
+                ("col_ids", ctypes.c_void_p)]
+
+
+class TimingsStruct(ctypes.Structure):
+    _fields_ = [("measure_all", ctypes.c_int), ("measure_complete", ctypes.c_int)] + [
+        (n, ctypes.c_float) for n in
+        ("init", "count_products", "load_balance_counting", "global_maps_counting",
+         "spgemm_counting", "alloc_c", "load_balance_numeric", "global_maps_numeric",
+         "spgemm_numeric", "sorting", "cleanup", "complete")]
+
+
+class StatsStruct(ctypes.Structure):
+    _fields_ = [("products", ctypes.c_uint64), ("nnz_c", ctypes.c_uint64),
+                ("max_row_products", ctypes.c_uint32),
+                ("class_rows", ctypes.c_uint32 * NUM_CLASSES),
+                ("kernel_launches", ctypes.c_uint32),
+                ("ms_analysis", ctypes.c_float), ("ms_symbolic", ctypes.c_float),
+                ("ms_scan", ctypes.c_float), ("ms_numeric", ctypes.c_float),
+                ("ms_total", ctypes.c_float), ("workspace_bytes", ctypes.c_uint64)]
+
+
+EXPORTS = [
+    "speck_b200_abi_version", "speck_b200_last_error", "speck_b200_create", "speck_b200_destroy",
+    "speck_b200_sm_count", "speck_b200_spgemm_f64", "speck_b200_spgemm_f32",
+    "speck_b200_spgemm_host_f64", "speck_b200_spgemm_host_f32", "speck_b200_get_stats",
+    "speck_b200_row_products", "speck_b200_compare_f64", "speck_b200_compare_f32",
+    "speck_b200_malloc", "speck_b200_free", "speck_b200_memcpy_h2d", "speck_b200_memcpy_d2h",
+    "speck_b200_free_csr", "speck_b200_synchronize", "speck_b200_stream", "speck_b200_set_option",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libspeck_b200.so; raises SpeckError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpeckError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(make -C speck_b200/csrc). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    P = ctypes.POINTER
+    vp = ctypes.c_void_p
+    lib.speck_b200_last_error.restype = ctypes.c_char_p
+    lib.speck_b200_create.argtypes = [ctypes.c_int, P(vp)]
+    lib.speck_b200_destroy.argtypes = [vp]
+    lib.speck_b200_sm_count.argtypes = [vp]
+    for n in ("speck_b200_spgemm_f64", "speck_b200_spgemm_f32"):
+        getattr(lib, n).argtypes = [vp, P(CsrStruct), P(CsrStruct), P(CsrStruct), P(TimingsStruct)]
+    for n in ("speck_b200_spgemm_host_f64", "speck_b200_spgemm_host_f32"):
+        getattr(lib, n).argtypes = [vp, P(CsrStruct), P(CsrStruct), P(CsrStruct),
+                                    P(ctypes.c_uint64), P(ctypes.c_uint64)]
+    lib.speck_b200_get_stats.argtypes = [vp, P(StatsStruct)]
+    lib.speck_b200_row_products.argtypes = [vp, P(CsrStruct), P(CsrStruct), vp,
+                                            P(ctypes.c_uint64), P(ctypes.c_uint32)]
+    for n in ("speck_b200_compare_f64", "speck_b200_compare_f32"):
+        getattr(lib, n).argtypes = [vp, P(CsrStruct), P(CsrStruct), ctypes.c_int, ctypes.c_double]
+    lib.speck_b200_malloc.argtypes = [vp, P(vp), ctypes.c_size_t]
+    lib.speck_b200_free.argtypes = [vp, vp]
+    lib.speck_b200_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.speck_b200_memcpy_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.speck_b200_free_csr.argtypes = [vp, P(CsrStruct)]
+    lib.speck_b200_synchronize.argtypes = [vp]
+    lib.speck_b200_stream.argtypes = [vp]
+    lib.speck_b200_stream.restype = vp
+    lib.speck_b200_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_longlong]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise SpeckError(f"speck_b200 error {rc}: {load_library().speck_b200_last_error().decode()}")
+    return rc
+
+
+class DeviceCSR:
+    """Device CSR (the reference's dCSR<T>): three cudaMalloc'ed arrays + sizes."""
+
+    def __init__(self, ctx, dtype=np.float64):
+        self.ctx = ctx
+        self.dtype = np.dtype(dtype)
+        self.s = CsrStruct(0, 0, 0, None, None, None)
+
+    rows = property(lambda self: self.s.rows)
+    cols = property(lambda self: self.s.cols)
+    nnz = property(lambda self: self.s.nnz)
+
+    def free(self):
+        if self.ctx is not None and self.ctx.h:
+            _check(self.ctx.lib.speck_b200_free_csr(self.ctx.h, ctypes.byref(self.s)))
+
+    def view(self, r0=None, r1=None):
+        """Borrowed struct (for passing as A/B)."""
+        return self.s
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        _check(self.lib.speck_b200_create(int(device), ctypes.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.speck_b200_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def sm_count(self):
+        return self.lib.speck_b200_sm_count(self.h)
+
+    def set_option(self, key, value):
+        _check(self.lib.speck_b200_set_option(self.h, key.encode(), int(value)))
+
+    # ---- convert(dCSR&, const CSR&) / convert(CSR&, const dCSR&)  (source/dCSR.cpp:50-76)
+    def _alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        _check(self.lib.speck_b200_malloc(self.h, ctypes.byref(p), nbytes))
+        return p
+
+    def upload(self, m: HostCSR) -> DeviceCSR:
+        d = DeviceCSR(self, m.data.dtype)
+        rp = np.ascontiguousarray(m.row_offsets, np.uint32)
+        ci = np.ascontiguousarray(m.col_ids, np.uint32)
+        v = np.ascontiguousarray(m.data)
+        d.s.rows, d.s.cols, d.s.nnz = m.rows, m.cols, m.nnz
+        d.s.row_offsets = self._alloc(rp.nbytes)
+        d.s.col_ids = self._alloc(ci.nbytes)
+        d.s.data = self._alloc(v.nbytes)
+        _check(self.lib.speck_b200_memcpy_h2d(self.h, d.s.row_offsets, rp.ctypes.data, rp.nbytes))
+        _check(self.lib.speck_b200_memcpy_h2d(self.h, d.s.col_ids, ci.ctypes.data, ci.nbytes))
+        _check(self.lib.speck_b200_memcpy_h2d(self.h, d.s.data, v.ctypes.data, v.nbytes))
+        return d
+
+    def download(self, d: DeviceCSR) -> HostCSR:
+        rows, nnz = d.s.rows, d.s.nnz
+        rp = np.zeros(rows + 1, np.uint32)
+        ci = np.zeros(nnz, np.uint32)
+        v = np.zeros(nnz, d.dtype)
+        if d.s.row_offsets:
+            _check(self.lib.speck_b200_memcpy_d2h(self.h, rp.ctypes.data, d.s.row_offsets, rp.nbytes))
+        if nnz:
+            _check(self.lib.speck_b200_memcpy_d2h(self.h, ci.ctypes.data, d.s.col_ids, ci.nbytes))
+            _check(self.lib.speck_b200_memcpy_d2h(self.h, v.ctypes.data, d.s.data, v.nbytes))
+        return HostCSR(rows, d.s.cols, rp, ci, v)
+
+    # ---- MultiplyspECK
+    def multiply(self, A: DeviceCSR, B: DeviceCSR, C: DeviceCSR = None, timings=None) -> DeviceCSR:
+        if C is None:
+            C = DeviceCSR(self, A.dtype)
+        fn = self.lib.speck_b200_spgemm_f32 if A.dtype == np.float32 else self.lib.speck_b200_spgemm_f64
+        t = timings if timings is not None else TimingsStruct()
+        _check(fn(self.h, ctypes.byref(A.s), ctypes.byref(B.s), ctypes.byref(C.s), ctypes.byref(t)))
+        return C
+
+    def multiply_host(self, A: HostCSR, B: HostCSR):
+        """End-to-end on host buffers -> (HostCSR view into the context's pinned output buffers,
+        h2d_bytes, d2h_bytes)."""
+        dt = np.dtype(A.data.dtype)
+        fn = self.lib.speck_b200_spgemm_host_f32 if dt == np.float32 else self.lib.speck_b200_spgemm_host_f64
+
+        def st(m):
+            return CsrStruct(m.rows, m.cols, m.nnz, m.data.ctypes.data, m.row_offsets.ctypes.data,
+                             m.col_ids.ctypes.data)
+        sa = st(A)
+        sb_ = sa if B is A else st(B)
+        sc = CsrStruct()
+        up, down = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _check(fn(self.h, ctypes.byref(sa), ctypes.byref(sb_), ctypes.byref(sc), ctypes.byref(up),
+                  ctypes.byref(down)))
+        rows, nnz = sc.rows, sc.nnz
+        if sc.row_offsets:
+            rp = np.ctypeslib.as_array(ctypes.cast(sc.row_offsets, ctypes.POINTER(ctypes.c_uint32)), (rows + 1,))
+        else:
+            rp = np.zeros(rows + 1, np.uint32)
+        if nnz:
+            ci = np.ctypeslib.as_array(ctypes.cast(sc.col_ids, ctypes.POINTER(ctypes.c_uint32)), (nnz,))
+            ct = ctypes.c_float if dt == np.float32 else ctypes.c_double
+            v = np.ctypeslib.as_array(ctypes.cast(sc.data, ctypes.POINTER(ct)), (nnz,))
+        else:
+            ci, v = np.zeros(0, np.uint32), np.zeros(0, dt)
+        return HostCSR(rows, sc.cols, rp, ci, v), int(up.value), int(down.value)
+
+    def stats(self):
+        s = StatsStruct()
+        _check(self.lib.speck_b200_get_stats(self.h, ctypes.byref(s)))
+        return {
+            "products": int(s.products), "nnz_c": int(s.nnz_c),
+            "max_row_products": int(s.max_row_products),
+            "class_rows": {BIN_NAMES[i]: int(s.class_rows[i]) for i in range(len(BIN_NAMES))},
+            "kernel_launches": int(s.kernel_launches),
+            "ms_analysis": s.ms_analysis, "ms_symbolic": s.ms_symbolic, "ms_scan": s.ms_scan,
+            "ms_numeric": s.ms_numeric, "ms_total": s.ms_total,
+            "workspace_bytes": int(s.workspace_bytes),
+        }
+
+    def row_products(self, A: DeviceCSR, B: DeviceCSR):
+        """-> (rowOps u32[rows], P, max) ; readOperations (include/common.cuh:321-459)."""
+        rows = A.rows
+        d = self._alloc(max(rows, 1) * 4)
+        P, mx = ctypes.c_uint64(0), ctypes.c_uint32(0)
+        try:
+            _check(self.lib.speck_b200_row_products(self.h, ctypes.byref(A.s), ctypes.byref(B.s), d,
+                                                    ctypes.byref(P), ctypes.byref(mx)))
+            out = np.zeros(rows, np.uint32)
+            if rows:
+                _check(self.lib.speck_b200_memcpy_d2h(self.h, out.ctypes.data, d, rows * 4))
+        finally:
+            self.lib.speck_b200_free(self.h, d)
+        return out, int(P.value), int(mx.value)
+
+    def compare(self, ref: DeviceCSR, cmp: DeviceCSR, compare_data=False, rel_tol=1e-6):
+        fn = self.lib.speck_b200_compare_f32 if ref.dtype == np.float32 else self.lib.speck_b200_compare_f64
+        return bool(_check(fn(self.h, ctypes.byref(ref.s), ctypes.byref(cmp.s), int(compare_data), float(rel_tol))))
+
+    def synchronize(self):
+        _check(self.lib.speck_b200_synchronize(self.h))
+
+
+def numeric_bytes(rows_a, nnz_a, products, nnz_c, val_bytes=8):
+    """Algorithmic bytes of the numeric phase:
+    8(rA+1) + 12 nnzA + 8 nnzA + 12 P + 12 nnzC for fp64 / u32 indices."""
+    iv = 4 + val_bytes
+    return 8 * (rows_a + 1) + iv * nnz_a + 8 * nnz_a + iv * products + iv * nnz_c
+
+
+def total_bytes(rows_a, nnz_a, products, nnz_c, val_bytes=8):
+    ana = 4 * (rows_a + 1) + 12 * nnz_a + 12 * rows_a
+    sym = 4 * (rows_a + 1) + 12 * nnz_a + 4 * products + 4 * rows_a
+    scan = 8 * (rows_a + 1)
+    return ana + sym + scan + numeric_bytes(rows_a, nnz_a, products, nnz_c, val_bytes)

@@ -1,0 +1,560 @@
+// speck_b200/csrc/capi.cu -- C ABI (include/speck_b200.h) and host orchestration of one multiply.
+//
+// Stage order and the reference stage each one replaces (source/GPU/Multiply.cu):
+//   analyze + bin      <- countProducts (:237-273) + loadBalanceCounting (:279-351)
+//   symbolic           <- globalMapsCounting + spGEMMCounting (:357-582), no global hash maps
+//   scan               <- cub::DeviceScan::ExclusiveSum (:570) + nnz read-back (:571-575)
+//   alloc C            <- allocC (:588-608), same reuse rules
+//   numeric            <- loadBalanceNumeric .. sorting (:614-1050); output is sorted in the
+//                         numeric kernels themselves, there is no separate sorting stage
+// Host<->device traffic per call: two 4-byte-class read-backs of one pinned Scalars struct
+// (after binning, after the scan) instead of the reference's 3-8 blocking copies, and no
+// cudaMalloc/cudaFree in the steady state (pooled workspace).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/speck_b200.h"
+#include "common.cuh"
+
+using namespace sb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(e__ == cudaErrorMemoryAllocation ? SPECK_ERR_OOM : SPECK_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int NSIDE = 4;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct speck_ctx {
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t main = nullptr;
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t evFork = nullptr, evJoin[NSIDE] = {};
+    cudaEvent_t evStage[6] = {};
+    Scalars *dSc = nullptr;
+    Scalars *hSc = nullptr;  // pinned
+    DevBuf rowOps, perm, tileState;
+    DevBuf stage[6];          // device staging of the *_host entry points (A: rp, ci, v; B: rp, ci, v)
+    void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
+    size_t hostOutCap[3] = {};
+    speck_csr hostC = {};     // device C kept across *_host calls (reuse rules)
+    u32 sortMax = SORT_MAX_PRODUCTS;
+    u32 launches = 0;
+    speck_stats stats = {};
+};
+
+namespace {
+
+int ensure(DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return SPECK_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SPECK_ERR_OOM, "workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return SPECK_OK;
+}
+
+void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+void fork_streams(speck_ctx *c)
+{
+    cudaEventRecord(c->evFork, c->main);
+    for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(c->side[i], c->evFork, 0);
+}
+
+void join_streams(speck_ctx *c)
+{
+    for (int i = 0; i < NSIDE; ++i) {
+        cudaEventRecord(c->evJoin[i], c->side[i]);
+        cudaStreamWaitEvent(c->main, c->evJoin[i], 0);
+    }
+}
+
+template <typename T>
+int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, speck_timings *tm)
+{
+    if (!c || !A || !B || !C) return fail(SPECK_ERR_INVALID, "null argument");
+    // guards of the reference, source/GPU/Multiply.cu:57-70
+    if (B->cols > (1u << 27)) return fail(SPECK_ERR_TOO_LARGE, "matrix B has more than %d columns (%zu)", 1 << 27, B->cols);
+    if (A->rows > (1u << 27)) return fail(SPECK_ERR_TOO_LARGE, "matrix A has more than %d rows (%zu)", 1 << 27, A->rows);
+    if (A->nnz == 0 || B->nnz == 0) {
+        C->nnz = 0;
+        c->stats = speck_stats{};
+        return SPECK_OK;
+    }
+    if (A->cols != B->rows) return fail(SPECK_ERR_INVALID, "shape mismatch: A is %zux%zu, B is %zux%zu", A->rows, A->cols, B->rows, B->cols);
+    if (!A->row_offsets || !A->col_ids || !A->data || !B->row_offsets || !B->col_ids || !B->data)
+        return fail(SPECK_ERR_INVALID, "null CSR array");
+
+    CU_TRY(cudaSetDevice(c->device));
+    const u32 rows = (u32)A->rows;
+    const u32 colsB = (u32)B->cols;
+    const u32 *aRp = A->row_offsets, *aCi = A->col_ids, *bRp = B->row_offsets, *bCi = B->col_ids;
+    const T *aV = (const T *)A->data, *bV = (const T *)B->data;
+    c->launches = 0;
+    LaunchCtx lc{c->main, c->smCount, &c->launches};
+
+    // ---- init: workspace, C.row_offsets (reuse rule of Multiply.cu:155-165)
+    cudaEventRecord(c->evStage[0], c->main);
+    int rc;
+    if ((rc = ensure(c->rowOps, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->perm, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->tileState, scan_tile_state_bytes(rows + 1)))) return rc;
+    u32 *cRp = C->row_offsets;
+    if (!(C->rows == A->rows && cRp != nullptr)) {
+        if (cRp) cudaFree(cRp);
+        C->row_offsets = nullptr;
+        CU_TRY(cudaMalloc(&cRp, (size_t)(rows + 1) * 4));
+        C->row_offsets = cRp;
+        C->rows = A->rows;
+    }
+    u32 *rowOps = (u32 *)c->rowOps.p, *perm = (u32 *)c->perm.p;
+    CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
+
+    // ---- analysis + binning
+    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, rowOps, cRp, c->dSc, c->sortMax);
+    launch_bin_scatter(lc, rows, aRp, rowOps, perm, c->dSc, c->sortMax);
+    CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
+    cudaEventRecord(c->evStage[1], c->main);
+    CU_TRY(cudaStreamSynchronize(c->main));
+    const Scalars s1 = *c->hSc;
+    if (s1.products == 0) {  // Multiply.cu:256-261: alloc(rows, cols, 0, false)
+        if (C->data) cudaFree(C->data);
+        if (C->col_ids) cudaFree(C->col_ids);
+        if (C->row_offsets) cudaFree(C->row_offsets);
+        C->data = nullptr; C->col_ids = nullptr; C->row_offsets = nullptr;
+        C->rows = A->rows; C->cols = B->cols; C->nnz = 0;
+        c->stats = speck_stats{};
+        return SPECK_OK;
+    }
+    u32 binStart[NUM_BINS + 1];
+    binStart[0] = 0;
+    for (int b = 0; b < NUM_BINS; ++b) binStart[b + 1] = binStart[b] + s1.binCount[b];
+
+    // ---- symbolic: dense rows first (longest), then the sort classes from large to small
+    fork_streams(c);
+    int sidx = 0;
+    {
+        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        launch_dense_symbolic(ls, perm + binStart[BIN_DENSE], s1.binCount[BIN_DENSE], &c->dSc->denseCounter[0], aRp,
+                              aCi, bRp, bCi, colsB, rowOps, cRp);
+    }
+    for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
+        const u32 cnt = s1.binCount[BIN_SORT0 + sc];
+        if (!cnt) continue;
+        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        launch_sort_symbolic(ls, sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, cRp);
+    }
+    join_streams(c);
+    cudaEventRecord(c->evStage[2], c->main);
+
+    // ---- scan + nnz read-back
+    launch_scan(lc, cRp, rows + 1, (u64 *)c->tileState.p, c->dSc);
+    CU_TRY(cudaMemcpyAsync(&c->hSc->nnzC, &c->dSc->nnzC, sizeof(u64), cudaMemcpyDeviceToHost, c->main));
+    cudaEventRecord(c->evStage[3], c->main);
+    CU_TRY(cudaStreamSynchronize(c->main));
+    CU_TRY(cudaGetLastError());
+    const u64 nnzC = c->hSc->nnzC;
+    if (nnzC > 0xffffffffull) return fail(SPECK_ERR_OVERFLOW, "nnz(C) = %llu does not fit the u32 row_offsets of the spECK API", (unsigned long long)nnzC);
+
+    // ---- alloc C (Multiply.cu:589-602): only when nnz changed
+    if (C->nnz != nnzC || !C->data || !C->col_ids) {
+        if (C->data) cudaFree(C->data);
+        if (C->col_ids) cudaFree(C->col_ids);
+        C->data = nullptr; C->col_ids = nullptr; C->nnz = 0;
+        cudaError_t e1 = cudaMalloc(&C->data, nnzC * sizeof(T));
+        cudaError_t e2 = cudaMalloc((void **)&C->col_ids, nnzC * sizeof(u32));
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            cudaGetLastError();
+            if (C->data) cudaFree(C->data);
+            if (C->col_ids) cudaFree(C->col_ids);
+            C->data = nullptr; C->col_ids = nullptr;
+            return fail(SPECK_ERR_OOM, "out of memory allocating C with %llu non-zeros", (unsigned long long)nnzC);
+        }
+    }
+    C->nnz = nnzC;
+    C->cols = B->cols;
+    u32 *cCi = C->col_ids;
+    T *cV = (T *)C->data;
+
+    // ---- numeric
+    cudaEventRecord(c->evStage[4], c->main);
+    fork_streams(c);
+    sidx = 0;
+    {
+        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        launch_dense_numeric<T>(ls, perm + binStart[BIN_DENSE], s1.binCount[BIN_DENSE], &c->dSc->denseCounter[1], aRp,
+                                aCi, aV, bRp, bCi, bV, colsB, rowOps, cRp, cCi, cV);
+    }
+    for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
+        const u32 cnt = s1.binCount[BIN_SORT0 + sc];
+        if (!cnt) continue;
+        const bool wide = ((u64)colsB << (2 + sc)) > (1ull << 32);
+        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
+                               cRp, cCi, cV);
+    }
+    {
+        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        launch_direct_numeric<T>(ls, perm + binStart[BIN_DIRECT], s1.binCount[BIN_DIRECT], aRp, aCi, aV, bRp, bCi, bV,
+                                 cRp, cCi, cV);
+    }
+    join_streams(c);
+    cudaEventRecord(c->evStage[5], c->main);
+    CU_TRY(cudaStreamSynchronize(c->main));
+    CU_TRY(cudaGetLastError());
+
+    // ---- stats / timings
+    speck_stats &st = c->stats;
+    st = speck_stats{};
+    st.products = s1.products;
+    st.nnz_c = nnzC;
+    st.max_row_products = s1.maxRowProducts;
+    for (int b = 0; b < NUM_BINS; ++b) st.class_rows[b] = s1.binCount[b];
+    st.kernel_launches = c->launches;
+    cudaEventElapsedTime(&st.ms_analysis, c->evStage[0], c->evStage[1]);
+    cudaEventElapsedTime(&st.ms_symbolic, c->evStage[1], c->evStage[2]);
+    cudaEventElapsedTime(&st.ms_scan, c->evStage[2], c->evStage[3]);
+    cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
+    cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
+    st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->tileState.cap;
+    if (tm) {
+        float allocMs = 0.f;
+        cudaEventElapsedTime(&allocMs, c->evStage[3], c->evStage[4]);
+        tm->init = 0.f;
+        tm->count_products = st.ms_analysis;
+        tm->load_balance_counting = 0.f;   // binning is fused into the analysis stage
+        tm->global_maps_counting = 0.f;    // no global hash maps exist
+        tm->spgemm_counting = st.ms_symbolic + st.ms_scan;
+        tm->alloc_c = allocMs;
+        tm->load_balance_numeric = 0.f;    // the same binning serves both phases
+        tm->global_maps_numeric = 0.f;
+        tm->spgemm_numeric = st.ms_numeric;
+        tm->sorting = 0.f;                 // rows are emitted sorted by the numeric kernels
+        tm->cleanup = 0.f;                 // pooled workspace, nothing to free
+        tm->complete = st.ms_total;
+    }
+    return SPECK_OK;
+}
+
+int ensure_host(speck_ctx *c, int i, size_t bytes)
+{
+    if (bytes <= c->hostOutCap[i]) return SPECK_OK;
+    if (c->hostOut[i]) cudaFreeHost(c->hostOut[i]);
+    c->hostOut[i] = nullptr;
+    c->hostOutCap[i] = 0;
+    size_t want = bytes + bytes / 16 + 4096;
+    cudaError_t e = cudaMallocHost(&c->hostOut[i], want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SPECK_ERR_OOM, "pinned host allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    c->hostOutCap[i] = want;
+    return SPECK_OK;
+}
+
+template <typename T>
+int spgemm_host_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, uint64_t *h2d, uint64_t *d2h)
+{
+    if (!c || !A || !B || !C) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    const bool alias = (A->row_offsets == B->row_offsets && A->col_ids == B->col_ids && A->data == B->data &&
+                        A->rows == B->rows && A->nnz == B->nnz);
+    uint64_t up = 0;
+    speck_csr dA = *A, dB = *B;
+    const speck_csr *src[2] = {A, B};
+    speck_csr *dst[2] = {&dA, &dB};
+    for (int m = 0; m < (alias ? 1 : 2); ++m) {
+        const speck_csr *h = src[m];
+        const size_t bytes[3] = {(h->rows + 1) * 4, h->nnz * 4, h->nnz * sizeof(T)};
+        const void *hp[3] = {h->row_offsets, h->col_ids, h->data};
+        for (int j = 0; j < 3; ++j) {
+            int rc = ensure(c->stage[m * 3 + j], bytes[j] ? bytes[j] : 4);
+            if (rc) return rc;
+            if (bytes[j]) CU_TRY(cudaMemcpyAsync(c->stage[m * 3 + j].p, hp[j], bytes[j], cudaMemcpyHostToDevice, c->main));
+            up += bytes[j];
+        }
+        dst[m]->row_offsets = (u32 *)c->stage[m * 3 + 0].p;
+        dst[m]->col_ids = (u32 *)c->stage[m * 3 + 1].p;
+        dst[m]->data = c->stage[m * 3 + 2].p;
+    }
+    if (alias) { dB = dA; dB.rows = B->rows; dB.cols = B->cols; }
+    int rc = spgemm_impl<T>(c, &dA, &dB, &c->hostC, nullptr);
+    if (rc) return rc;
+    const speck_csr &dC = c->hostC;
+    uint64_t down = 0;
+    C->rows = A->rows; C->cols = B->cols; C->nnz = dC.nnz;
+    C->row_offsets = nullptr; C->col_ids = nullptr; C->data = nullptr;
+    if (dC.row_offsets) {
+        const size_t bytes[3] = {(dC.rows + 1) * 4, dC.nnz * 4, dC.nnz * sizeof(T)};
+        const void *dp[3] = {dC.row_offsets, dC.col_ids, dC.data};
+        for (int j = 0; j < 3; ++j) {
+            if ((rc = ensure_host(c, j, bytes[j] ? bytes[j] : 4))) return rc;
+            if (bytes[j]) CU_TRY(cudaMemcpyAsync(c->hostOut[j], dp[j], bytes[j], cudaMemcpyDeviceToHost, c->main));
+            down += bytes[j];
+        }
+        CU_TRY(cudaStreamSynchronize(c->main));
+        C->row_offsets = (u32 *)c->hostOut[0];
+        C->col_ids = (u32 *)c->hostOut[1];
+        C->data = c->hostOut[2];
+    }
+    if (h2d) *h2d = up;
+    if (d2h) *d2h = down;
+    return SPECK_OK;
+}
+
+template <typename T>
+int compare_impl(speck_ctx *c, const speck_csr *ref, const speck_csr *cmp, int compareData, double relTol)
+{
+    if (!c || !ref || !cmp) return fail(SPECK_ERR_INVALID, "null argument");
+    if (ref->rows != cmp->rows || ref->cols != cmp->cols || ref->nnz != cmp->nnz) return 0;
+    if (ref->nnz == 0) return 1;
+    if (!ref->row_offsets || !cmp->row_offsets || !ref->col_ids || !cmp->col_ids) return 0;
+    if (compareData && (!ref->data || !cmp->data)) return fail(SPECK_ERR_INVALID, "compare_data set but a value array is null");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMemsetAsync(&c->dSc->compareFlag, 0, 4, c->main));
+    u32 n = 0;
+    LaunchCtx lc{c->main, c->smCount, &n};
+    launch_compare<T>(lc, (u32)ref->rows, ref->row_offsets, ref->col_ids, (const T *)ref->data, cmp->row_offsets,
+                      cmp->col_ids, (const T *)cmp->data, compareData != 0, relTol, c->dSc);
+    CU_TRY(cudaMemcpyAsync(&c->hSc->compareFlag, &c->dSc->compareFlag, 4, cudaMemcpyDeviceToHost, c->main));
+    CU_TRY(cudaStreamSynchronize(c->main));
+    CU_TRY(cudaGetLastError());
+    return c->hSc->compareFlag == 0 ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int speck_b200_abi_version(void) { return SPECK_B200_ABI_VERSION; }
+const char *speck_b200_last_error(void) { return g_err; }
+
+int speck_b200_create(int device, speck_ctx **out)
+{
+    if (!out) return fail(SPECK_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SPECK_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(SPECK_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SPECK_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor);
+    CU_TRY(cudaSetDevice(device));
+    speck_ctx *c = new (std::nothrow) speck_ctx();
+    if (!c) return fail(SPECK_ERR_OOM, "host allocation failed");
+    c->device = device;
+    c->smCount = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking));
+    for (int i = 0; i < NSIDE; ++i) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&c->evJoin[i], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    for (auto &e : c->evStage) CU_TRY(cudaEventCreate(&e));
+    CU_TRY(cudaMalloc(&c->dSc, sizeof(Scalars)));
+    CU_TRY(cudaMallocHost(&c->hSc, sizeof(Scalars)));
+    *out = c;
+    return SPECK_OK;
+}
+
+int speck_b200_destroy(speck_ctx *c)
+{
+    if (!c) return SPECK_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    release(c->rowOps); release(c->perm); release(c->tileState);
+    for (auto &b : c->stage) release(b);
+    for (auto &h : c->hostOut) if (h) cudaFreeHost(h);
+    if (c->hostC.data) cudaFree(c->hostC.data);
+    if (c->hostC.col_ids) cudaFree(c->hostC.col_ids);
+    if (c->hostC.row_offsets) cudaFree(c->hostC.row_offsets);
+    if (c->dSc) cudaFree(c->dSc);
+    if (c->hSc) cudaFreeHost(c->hSc);
+    for (auto &e : c->evStage) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < NSIDE; ++i) {
+        if (c->evJoin[i]) cudaEventDestroy(c->evJoin[i]);
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    }
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->main) cudaStreamDestroy(c->main);
+    delete c;
+    return SPECK_OK;
+}
+
+int speck_b200_sm_count(const speck_ctx *c) { return c ? c->smCount : 0; }
+
+int speck_b200_spgemm_f64(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, speck_timings *t)
+{
+    return spgemm_impl<double>(c, A, B, C, t);
+}
+int speck_b200_spgemm_f32(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, speck_timings *t)
+{
+    return spgemm_impl<float>(c, A, B, C, t);
+}
+int speck_b200_spgemm_host_f64(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, uint64_t *h2d, uint64_t *d2h)
+{
+    return spgemm_host_impl<double>(c, A, B, C, h2d, d2h);
+}
+int speck_b200_spgemm_host_f32(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, uint64_t *h2d, uint64_t *d2h)
+{
+    return spgemm_host_impl<float>(c, A, B, C, h2d, d2h);
+}
+
+int speck_b200_get_stats(const speck_ctx *c, speck_stats *out)
+{
+    if (!c || !out) return fail(SPECK_ERR_INVALID, "null argument");
+    *out = c->stats;
+    return SPECK_OK;
+}
+
+int speck_b200_row_products(speck_ctx *c, const speck_csr *A, const speck_csr *B, uint32_t *dRowOps, uint64_t *products, uint32_t *maxRow)
+{
+    if (!c || !A || !B) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    if (products) *products = 0;
+    if (maxRow) *maxRow = 0;
+    if (A->rows == 0 || A->nnz == 0 || B->nnz == 0) {
+        if (dRowOps && A->rows) CU_TRY(cudaMemsetAsync(dRowOps, 0, A->rows * 4, c->main));
+        CU_TRY(cudaStreamSynchronize(c->main));
+        return SPECK_OK;
+    }
+    const u32 rows = (u32)A->rows;
+    int rc;
+    if ((rc = ensure(c->rowOps, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->perm, (size_t)rows * 4))) return rc;  // scratch for the rowNnz side output
+    CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
+    u32 n = 0;
+    LaunchCtx lc{c->main, c->smCount, &n};
+    launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, (u32 *)c->rowOps.p, (u32 *)c->perm.p,
+                   c->dSc, c->sortMax);
+    if (dRowOps) CU_TRY(cudaMemcpyAsync(dRowOps, c->rowOps.p, (size_t)rows * 4, cudaMemcpyDeviceToDevice, c->main));
+    CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
+    CU_TRY(cudaStreamSynchronize(c->main));
+    CU_TRY(cudaGetLastError());
+    if (products) *products = c->hSc->products;
+    if (maxRow) *maxRow = c->hSc->maxRowProducts;
+    return SPECK_OK;
+}
+
+int speck_b200_compare_f64(speck_ctx *c, const speck_csr *r, const speck_csr *m, int cd, double tol)
+{
+    return compare_impl<double>(c, r, m, cd, tol);
+}
+int speck_b200_compare_f32(speck_ctx *c, const speck_csr *r, const speck_csr *m, int cd, double tol)
+{
+    return compare_impl<float>(c, r, m, cd, tol);
+}
+
+int speck_b200_malloc(speck_ctx *c, void **dptr, size_t bytes)
+{
+    if (!c || !dptr) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    *dptr = nullptr;
+    CU_TRY(cudaMalloc(dptr, bytes ? bytes : 4));
+    return SPECK_OK;
+}
+int speck_b200_free(speck_ctx *c, void *dptr)
+{
+    if (!c) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    if (dptr) CU_TRY(cudaFree(dptr));
+    return SPECK_OK;
+}
+int speck_b200_memcpy_h2d(speck_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    if (bytes) CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->main));
+    CU_TRY(cudaStreamSynchronize(c->main));
+    return SPECK_OK;
+}
+int speck_b200_memcpy_d2h(speck_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    if (bytes) CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->main));
+    CU_TRY(cudaStreamSynchronize(c->main));
+    return SPECK_OK;
+}
+int speck_b200_free_csr(speck_ctx *c, speck_csr *C)
+{
+    if (!c || !C) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    if (C->data) cudaFree(C->data);
+    if (C->col_ids) cudaFree(C->col_ids);
+    if (C->row_offsets) cudaFree(C->row_offsets);
+    memset(C, 0, sizeof(*C));
+    return SPECK_OK;
+}
+int speck_b200_synchronize(speck_ctx *c)
+{
+    if (!c) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaDeviceSynchronize());
+    return SPECK_OK;
+}
+void *speck_b200_stream(speck_ctx *c) { return c ? (void *)c->main : nullptr; }
+
+int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
+{
+    if (!c || !key) return fail(SPECK_ERR_INVALID, "null argument");
+    if (!strcmp(key, "sort_max")) {
+        if (value < 4 || value > (long long)SORT_MAX_PRODUCTS || (value & (value - 1)))
+            return fail(SPECK_ERR_INVALID, "sort_max must be a power of two in [4, %u]", SORT_MAX_PRODUCTS);
+        c->sortMax = (u32)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "release_workspace")) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        release(c->rowOps); release(c->perm); release(c->tileState);
+        for (auto &b : c->stage) release(b);
+        return SPECK_OK;
+    }
+    return fail(SPECK_ERR_INVALID, "unknown option '%s'", key);
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// speck_b200/csrc/common.cuh -- shared definitions of the sm_100a SpGEMM kernels.
+//
+// Pipeline (replaces source/GPU/Multiply.cu:99-1122 of the reference):
+//   analyze rows -> bin rows by product count -> symbolic (exact nnz per row) ->
+//   decoupled look-back scan (row_ptr) -> numeric (sorted col/val assembly).
+// Row classes ("bins"):
+//   BIN_DIRECT        A row has exactly one entry: C row = scaled copy of one B row
+//                     (reference: directSpGEMM*, spECK_HashSpGEMM.cuh:543-589)
+//   BIN_SORT0 + c     products <= 4<<c (c = 0..8): register bitonic sort of the row's
+//                     products by a lane group, duplicates folded after the sort
+//                     (replaces the smem hash + O(n^2) rank sort, :591-866)
+//   BIN_DENSE         more products: CTA per row, sparse-cleared column bitmap in
+//                     shared memory, popcount ranks give the sorted position of every
+//                     product, values accumulate with fp RED into C
+//                     (replaces denseSpGEMM{Count,Numeric}, :1300-1711)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+namespace sb {
+
+constexpr int NUM_SORT = 9;                 // sort classes: 4, 8, ..., 1024 products
+constexpr int BIN_DIRECT = 0;
+constexpr int BIN_SORT0 = 1;
+constexpr int BIN_DENSE = BIN_SORT0 + NUM_SORT;   // 10
+constexpr int NUM_BINS = BIN_DENSE + 1;           // 11
+constexpr u32 SORT_MAX_PRODUCTS = 4u << (NUM_SORT - 1);  // 1024
+
+// Device-resident scalars of one multiply; mirrored into pinned host memory.
+struct Scalars {
+    u64 products;             // P (u64: the reference's u32 sumProducts overflows, Multiply.cu:237-252)
+    u64 nnzC;                 // total of the row_ptr scan
+    u32 maxRowProducts;
+    u32 binCount[NUM_BINS];   // rows per bin (written by k_analyze)
+    u32 binCursor[NUM_BINS];  // scatter cursors (k_bin_scatter)
+    u32 denseCounter[2];      // dynamic row queues of the dense kernels (symbolic, numeric)
+    u32 tileCounter;          // dynamic tile ids of the scan
+    u32 compareFlag;          // k_compare: 0 = equal
+};
+
+struct CsrView {
+    const u32 *rp;
+    const u32 *ci;
+    const void *v;
+};
+
+// bin of a row; -1 = no products at all
+__host__ __device__ __forceinline__ int classify_row(u32 ops, u32 aLen, u32 sortMax)
+{
+    if (ops == 0) return -1;
+    if (aLen == 1) return BIN_DIRECT;
+    if (ops > sortMax) return BIN_DENSE;
+    int c = 0;
+    while ((4u << c) < ops) ++c;
+    return BIN_SORT0 + c;
+}
+
+// ---------------------------------------------------------------- launch API (host)
+struct LaunchCtx {
+    cudaStream_t stream;
+    int smCount;
+    u32 *launches;   // incremented per kernel launch
+};
+
+void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
+                    u32 *rowOps, u32 *rowNnz, Scalars *sc, u32 sortMax);
+void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, u32 *perm,
+                        Scalars *sc, u32 sortMax);
+void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trailing total slot */,
+                 u64 *tileState, Scalars *sc);
+size_t scan_tile_state_bytes(u32 n);
+
+void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, const u32 *perm, u32 count, const u32 *aRp,
+                          const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, u32 *rowNnz);
+template <typename T>
+void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
+                         const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi,
+                         const T *bV, const u32 *rowOps, const u32 *cRp, u32 *cCi, T *cV);
+template <typename T>
+void launch_direct_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
+                           const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *cRp,
+                           u32 *cCi, T *cV);
+
+// dense (bitmap) path; winBits = log2 of the column window held in shared memory
+int dense_window_bits(u64 colsB);
+void launch_dense_symbolic(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
+                           const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB, const u32 *rowOps,
+                           u32 *rowNnz);
+template <typename T>
+void launch_dense_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
+                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
+                          u32 colsB, const u32 *rowOps, const u32 *cRp, u32 *cCi, T *cV);
+
+template <typename T>
+void launch_compare(const LaunchCtx &lc, u32 rows, const u32 *rpA, const u32 *ciA, const T *vA, const u32 *rpB,
+                    const u32 *ciB, const T *vB, bool compareData, double relTol, Scalars *sc);
+
+}  // namespace sb

@@ -1,0 +1,290 @@
+// speck_b200/csrc/kernels_dense.cu -- "dense" row class: one CTA per row of C, column bitmap in
+// shared memory.
+//
+// Replaces denseSpGEMMCount / denseSpGEMMNumeric and the class-0/1/2 hash kernels of the
+// reference (include/GPU/spECK_HashSpGEMM.cuh:1300-1711, 591-866) for rows with more products
+// than the sort classes take.  Differences by design (B200: 227 KB shared memory per CTA):
+//   * the bitmap covers a window of up to 2^20 columns (128 KB) instead of a ~5.8 k-column dense
+//     value window, so most matrices need ONE pass per row instead of range/5.8k passes;
+//   * the bitmap is cleared sparsely: a summary bit per 128-column chunk records which chunks
+//     were touched, so per-row cost is O(products), not O(column range);
+//   * sorted output comes from popcount ranks (chunk prefix + in-chunk popc), values are
+//     accumulated with fp RED (red.global.add) straight into the zero-initialised C row, so no
+//     value window, no shared-memory CAS loops and no separate sorting pass are needed.
+// Rows are pulled from a device-side queue (atomic counter), CTAs are persistent.
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int CHUNK_WORDS = 4;       // 128 columns per chunk = one 16-byte shared load
+constexpr int DENSE_MAX_WIN_BITS = 20;
+constexpr int DENSE_MIN_WIN_BITS = 12;  // 4096 columns = 32 chunks = one summary word
+
+int dense_window_bits(u64 colsB)
+{
+    int b = DENSE_MIN_WIN_BITS;
+    while (b < DENSE_MAX_WIN_BITS && (1ull << b) < colsB) ++b;
+    return b;
+}
+
+static size_t dense_smem_bytes(int winBits)
+{
+    const size_t words = (size_t)1 << (winBits - 5);
+    const size_t chunks = words / CHUNK_WORDS;
+    const size_t sum = chunks / 32 ? chunks / 32 : 1;
+    return (words + chunks + sum) * sizeof(u32);
+}
+
+__device__ __forceinline__ u32 lower_bound_dev(const u32 *__restrict__ a, u32 lo, u32 hi, u32 key)
+{
+    while (lo < hi) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// exclusive scan of one u32 per thread; returns the exclusive prefix, *total = block sum.
+template <int THREADS>
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *sWarp, u32 *total)
+{
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (u32)d) incl += t;
+    }
+    __syncthreads();  // sWarp may still be read from a previous use
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    constexpr int NW = THREADS / 32;
+    u32 wv = (lane < NW) ? sWarp[lane] : 0u;
+    u32 winc = wv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= (u32)d) winc += t;
+    }
+    const u32 warpBase = __shfl_sync(0xffffffffu, winc - wv, warp);
+    *total = __shfl_sync(0xffffffffu, winc, NW - 1);
+    return warpBase + incl - v;
+}
+
+template <int THREADS, typename T, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS)
+k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, const u32 *__restrict__ aRp,
+             const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
+             const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 colsB, const int winBits,
+             const u32 *__restrict__ rowOps, u32 *cRp, u32 *__restrict__ cCi, T *cV)
+{
+    extern __shared__ __align__(16) u32 dsm[];
+    const u32 W = 1u << winBits;
+    const u32 WWORDS = W >> 5;
+    const u32 NCHUNK = WWORDS / CHUNK_WORDS;
+    const u32 NSUM = NCHUNK / 32 ? NCHUNK / 32 : 1;
+    u32 *bitmap = dsm;
+    u32 *chunkPrefix = bitmap + WWORDS;
+    u32 *summary = chunkPrefix + NCHUNK;
+    __shared__ u32 sWarp[32];
+    __shared__ u32 sRow, sMin, sMax;
+
+    const u32 tid = threadIdx.x;
+    for (u32 i = tid; i < WWORDS; i += THREADS) bitmap[i] = 0;
+    for (u32 i = tid; i < NSUM; i += THREADS) summary[i] = 0;
+    const u32 numWin = (colsB + W - 1) >> winBits;
+    const u32 CPT = (NCHUNK + THREADS - 1) / THREADS;  // consecutive chunks per thread
+    const u32 chBeg = tid * CPT;
+    const u32 chEnd = min(NCHUNK, chBeg + CPT);
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) { sRow = atomicAdd(rowCounter, 1u); sMin = 0xffffffffu; sMax = 0u; }
+        __syncthreads();
+        const u32 ri = sRow;
+        if (ri >= count) break;
+        const u32 row = perm[ri];
+        const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
+        const u32 ops = rowOps[row];
+        // lanes per B row: largest power of two <= average B-row length, in [4, 32]
+        const u32 avg = ops / (aEnd - aBeg);
+        int shift = 5;
+        while (shift > 2 && (1u << shift) > avg) --shift;
+        const u32 LPR = 1u << shift;
+        const u32 groups = THREADS >> shift;
+        const u32 g = tid >> shift, gl = tid & (LPR - 1);
+
+        u32 winFirst = 0, winLast = 0;
+        if (numWin > 1) {  // column extent of the row -> windows to visit
+            u32 mn = 0xffffffffu, mx = 0u;
+            for (u32 a = aBeg + tid; a < aEnd; a += THREADS) {
+                const u32 k = __ldg(aCi + a);
+                const u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
+                if (be > bs) { mn = min(mn, __ldg(bCi + bs)); mx = max(mx, __ldg(bCi + be - 1)); }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            }
+            if ((tid & 31) == 0) { atomicMin(&sMin, mn); atomicMax(&sMax, mx); }
+            __syncthreads();
+            winFirst = sMin >> winBits;
+            winLast = sMax >> winBits;
+        }
+        const u32 rowStart = NUMERIC ? cRp[row] : 0u;
+        u32 winBase = 0;
+
+        for (u32 win = winFirst; win <= winLast; ++win) {
+            const u32 winLo = win << winBits;
+            const u32 winHi = min(colsB, winLo + W);
+            // ------------------------------------------------ pass A: set column bits
+            for (u32 a = aBeg + g; a < aEnd; a += groups) {
+                const u32 k = __ldg(aCi + a);
+                u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
+                if (numWin > 1) {
+                    bs = lower_bound_dev(bCi, bs, be, winLo);
+                    be = lower_bound_dev(bCi, bs, be, winHi);
+                }
+                for (u32 q = bs + gl; q < be; q += LPR) {
+                    const u32 c = __ldg(bCi + q) - winLo;
+                    const u32 w = c >> 5;
+                    const u32 old = atomicOr(&bitmap[w], 1u << (c & 31));
+                    if (old == 0) atomicOr(&summary[w >> 7], 1u << ((w >> 2) & 31));
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------ chunk counts (touched chunks only)
+            u32 tsum = 0;
+            for (u32 ch = chBeg; ch < chEnd; ++ch) {
+                if ((summary[ch >> 5] >> (ch & 31)) & 1u) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(&bitmap[ch * CHUNK_WORDS]);
+                    if (NUMERIC) chunkPrefix[ch] = tsum;
+                    tsum += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                }
+            }
+            u32 winTotal;
+            const u32 texcl = block_exclusive_scan<THREADS>(tsum, sWarp, &winTotal);
+
+            if (NUMERIC) {
+                // -------------------------------------------- final prefixes + sorted column ids
+                for (u32 ch = chBeg; ch < chEnd; ++ch) {
+                    if ((summary[ch >> 5] >> (ch & 31)) & 1u) {
+                        const u32 pfx = chunkPrefix[ch] + texcl + winBase;
+                        chunkPrefix[ch] = pfx;
+                        u32 pos = rowStart + pfx;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(&bitmap[ch * CHUNK_WORDS]);
+                        const u32 wv[4] = {v.x, v.y, v.z, v.w};
+                        const u32 colBase = winLo + ch * (CHUNK_WORDS * 32);
+#pragma unroll
+                        for (int wi = 0; wi < 4; ++wi) {
+                            u32 bits = wv[wi];
+                            while (bits) {
+                                const u32 b = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                cCi[pos++] = colBase + wi * 32 + b;
+                            }
+                        }
+                    }
+                }
+                // -------------------------------------------- zero the value slots of this window
+                for (u32 j = tid; j < winTotal; j += THREADS) cV[rowStart + winBase + j] = (T)0;
+                __threadfence_block();
+                __syncthreads();
+                // -------------------------------------------- pass B: rank + RED
+                for (u32 a = aBeg + g; a < aEnd; a += groups) {
+                    const u32 k = __ldg(aCi + a);
+                    const T av = __ldg(aV + a);
+                    u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
+                    if (numWin > 1) {
+                        bs = lower_bound_dev(bCi, bs, be, winLo);
+                        be = lower_bound_dev(bCi, bs, be, winHi);
+                    }
+                    for (u32 q = bs + gl; q < be; q += LPR) {
+                        const u32 c = __ldg(bCi + q) - winLo;
+                        const T prod = av * __ldg(bV + q);
+                        const u32 w = c >> 5;
+                        const u32 ch = w >> 2;
+                        const u32 wi = w & 3;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(&bitmap[ch * CHUNK_WORDS]);
+                        const u32 below = (wi > 0 ? __popc(v.x) : 0) + (wi > 1 ? __popc(v.y) : 0) +
+                                          (wi > 2 ? __popc(v.z) : 0);
+                        const u32 word = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
+                        const u32 rank = chunkPrefix[ch] + below + __popc(word & ((1u << (c & 31)) - 1u));
+                        atomicAdd(&cV[rowStart + rank], prod);
+                    }
+                }
+                __syncthreads();
+            }
+            // ------------------------------------------------ sparse clear
+            for (u32 ch = chBeg; ch < chEnd; ++ch) {
+                if ((summary[ch >> 5] >> (ch & 31)) & 1u)
+                    *reinterpret_cast<uint4 *>(&bitmap[ch * CHUNK_WORDS]) = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            for (u32 i = tid; i < NSUM; i += THREADS) summary[i] = 0;
+            __syncthreads();
+            winBase += winTotal;
+        }
+        if (!NUMERIC && tid == 0) cRp[row] = winBase;
+    }
+}
+
+template <int THREADS, typename T, bool NUMERIC>
+static void launch_dense_t(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
+                           const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, u32 colsB,
+                           const u32 *rowOps, u32 *cRp, u32 *cCi, T *cV)
+{
+    const int winBits = dense_window_bits(colsB);
+    const size_t smem = dense_smem_bytes(winBits);
+    auto kern = k_dense_rows<THREADS, T, NUMERIC>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int perSm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, THREADS, smem);
+    if (perSm < 1) perSm = 1;
+    u32 grid = (u32)(lc.smCount * perSm);
+    if (grid > count) grid = count;
+    kern<<<grid, THREADS, smem, lc.stream>>>(perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, colsB, winBits,
+                                             rowOps, cRp, cCi, cV);
+    ++*lc.launches;
+}
+
+// CTA size: big windows leave room for one CTA per SM -> 1024 threads; small windows -> 256.
+static bool dense_big_cta(u64 colsB) { return dense_window_bits(colsB) >= 19; }
+
+void launch_dense_symbolic(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
+                           const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB, const u32 *rowOps,
+                           u32 *rowNnz)
+{
+    if (count == 0) return;
+    const float *nv = nullptr;
+    if (dense_big_cta(colsB))
+        launch_dense_t<1024, float, false>(lc, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv, colsB, rowOps,
+                                           rowNnz, nullptr, nullptr);
+    else
+        launch_dense_t<256, float, false>(lc, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv, colsB, rowOps,
+                                          rowNnz, nullptr, nullptr);
+}
+
+template <typename T>
+void launch_dense_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
+                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
+                          u32 colsB, const u32 *rowOps, const u32 *cRp, u32 *cCi, T *cV)
+{
+    if (count == 0) return;
+    u32 *rp = const_cast<u32 *>(cRp);
+    if (dense_big_cta(colsB))
+        launch_dense_t<1024, T, true>(lc, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, colsB, rowOps, rp,
+                                      cCi, cV);
+    else
+        launch_dense_t<256, T, true>(lc, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, colsB, rowOps, rp,
+                                     cCi, cV);
+}
+template void launch_dense_numeric<double>(const LaunchCtx &, const u32 *, u32, u32 *, const u32 *, const u32 *,
+                                           const double *, const u32 *, const u32 *, const double *, u32,
+                                           const u32 *, const u32 *, u32 *, double *);
+template void launch_dense_numeric<float>(const LaunchCtx &, const u32 *, u32, u32 *, const u32 *, const u32 *,
+                                          const float *, const u32 *, const u32 *, const float *, u32,
+                                          const u32 *, const u32 *, u32 *, float *);
+
+}  // namespace sb

@@ -1,0 +1,328 @@
+// speck_b200/csrc/kernels_misc.cu -- row analysis, binning, row_ptr scan, direct rows, compare.
+#include "common.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------
+// Row analysis.  Replaces readOperations (reference include/common.cuh:321-459):
+//   rowOps[i] = sum_{k in A_i} nnz(B_k)   (upper bound of nnz(C_i), exact product count)
+//   P (u64 atomic), max over rows, and -- new -- the bin histogram, so that no host
+//   round trip is needed to classify (reference: Multiply.cu:263-345 on the host).
+// LA lanes cooperate on one row; A.col_idx is read coalesced across the lane group.
+// Rows without products get rowNnz = 0 here; one-entry rows get rowNnz = nnz(B_k) (they
+// skip the symbolic phase, as directSpGEMMCount does, spECK_HashSpGEMM.cuh:572-589).
+// ------------------------------------------------------------------------------------------
+template <int LA>
+__global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict__ aRp,
+                                                 const u32 *__restrict__ aCi,
+                                                 const u32 *__restrict__ bRp, u32 *__restrict__ rowOps,
+                                                 u32 *__restrict__ rowNnz, Scalars *sc, u32 sortMax)
+{
+    __shared__ u32 sBin[NUM_BINS];
+    __shared__ unsigned long long sProd;
+    __shared__ u32 sMax;
+    if (threadIdx.x < NUM_BINS) sBin[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { sProd = 0; sMax = 0; }
+    __syncthreads();
+
+    const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 row = gtid / LA;
+    const u32 lane = threadIdx.x % LA;
+    u64 ops64 = 0;
+    u32 aLen = 0;
+    if (row < rows) {
+        const u32 beg = aRp[row], end = aRp[row + 1];
+        aLen = end - beg;
+        for (u32 p = beg + lane; p < end; p += LA) {
+            const u32 k = __ldg(aCi + p);
+            ops64 += (u64)(__ldg(bRp + k + 1) - __ldg(bRp + k));
+        }
+    }
+#pragma unroll
+    for (int d = LA / 2; d >= 1; d >>= 1) ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
+    const u32 ops = ops64 > 0xffffffffull ? 0xffffffffu : (u32)ops64;
+
+    u64 myProd = 0;
+    u32 myMax = 0;
+    if (row < rows && lane == 0) {
+        rowOps[row] = ops;
+        const int bin = classify_row(ops, aLen, sortMax);
+        if (bin < 0)
+            rowNnz[row] = 0;
+        else {
+            if (bin == BIN_DIRECT) rowNnz[row] = ops;
+            atomicAdd(&sBin[bin], 1u);
+        }
+        myProd = ops64;
+        myMax = ops;
+    }
+    // warp reduce, then one shared atomic per warp, one global atomic per block
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        myProd += __shfl_xor_sync(0xffffffffu, myProd, d);
+        myMax = max(myMax, __shfl_xor_sync(0xffffffffu, myMax, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (myProd) atomicAdd(&sProd, (unsigned long long)myProd);
+        if (myMax) atomicMax(&sMax, myMax);
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_BINS && sBin[threadIdx.x]) atomicAdd(&sc->binCount[threadIdx.x], sBin[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (sProd) atomicAdd((unsigned long long *)&sc->products, sProd);
+        if (sMax) atomicMax(&sc->maxRowProducts, sMax);
+    }
+}
+
+void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
+                    u32 *rowOps, u32 *rowNnz, Scalars *sc, u32 sortMax)
+{
+    if (rows == 0) return;
+    const double avg = (double)nnzA / (double)rows;
+    const int threads = 256;
+    if (avg <= 3.0) {
+        const u32 grid = (u32)(((u64)rows * 2 + threads - 1) / threads);
+        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, rowOps, rowNnz, sc, sortMax);
+    } else if (avg <= 24.0) {
+        const u32 grid = (u32)(((u64)rows * 8 + threads - 1) / threads);
+        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, rowOps, rowNnz, sc, sortMax);
+    } else {
+        const u32 grid = (u32)(((u64)rows * 32 + threads - 1) / threads);
+        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, rowOps, rowNnz, sc, sortMax);
+    }
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// Binning: scatter row ids into one permutation array ordered by bin.  Replaces the load
+// balancer (reference spECK_HashLoadBalancer.cuh:265-347 + scan_largearray_kernel.cuh:182-281
+// + the <=6 D2D memcpys): one pass, one global atomic per (block, bin).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__restrict__ aRp,
+                                                     const u32 *__restrict__ rowOps, u32 *__restrict__ perm,
+                                                     Scalars *sc, u32 sortMax)
+{
+    __shared__ u32 sCnt[NUM_BINS];
+    __shared__ u32 sBase[NUM_BINS];
+    if (threadIdx.x < NUM_BINS) sCnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    int bin = -1;
+    u32 rank = 0;
+    if (row < rows) {
+        bin = classify_row(rowOps[row], aRp[row + 1] - aRp[row], sortMax);
+        if (bin >= 0) rank = atomicAdd(&sCnt[bin], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_BINS) {
+        u32 start = 0;
+        for (int b = 0; b < (int)threadIdx.x; ++b) start += sc->binCount[b];
+        const u32 c = sCnt[threadIdx.x];
+        sBase[threadIdx.x] = start + (c ? atomicAdd(&sc->binCursor[threadIdx.x], c) : 0u);
+    }
+    __syncthreads();
+    if (bin >= 0) perm[sBase[bin] + rank] = row;
+}
+
+void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, u32 *perm,
+                        Scalars *sc, u32 sortMax)
+{
+    if (rows == 0) return;
+    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, perm, sc, sortMax);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// row_ptr scan: single-pass exclusive scan with decoupled look-back, in place.
+// Replaces cub::DeviceScan::ExclusiveSum (reference Multiply.cu:570).  data[n-1] is the
+// trailing slot (its input is ignored and treated as 0, so it receives the total = nnz(C)).
+// Tile state word: bits 63..62 = flag (0 empty, 1 aggregate, 2 inclusive prefix), rest value.
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr u64 FLAG_AGG = 1ull << 62;
+constexpr u64 FLAG_PFX = 2ull << 62;
+constexpr u64 VALUE_MASK = (1ull << 62) - 1;
+
+size_t scan_tile_state_bytes(u32 n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1) * sizeof(u64); }
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(u32 *__restrict__ data, u32 n,
+                                                       volatile u64 *tileState, Scalars *sc)
+{
+    __shared__ u32 sTile;
+    __shared__ u64 sWarpSum[SCAN_THREADS / 32];
+    __shared__ u64 sExclusive;
+    if (threadIdx.x == 0) sTile = atomicAdd(&sc->tileCounter, 1u);
+    __syncthreads();
+    const u32 tile = sTile;
+    const u32 base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+
+    u32 items[SCAN_ITEMS];
+    u64 tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const u32 idx = base + i;
+        items[i] = (idx < n - 1) ? data[idx] : 0u;  // trailing slot and out-of-range count as 0
+        tsum += items[i];
+    }
+    // block inclusive scan of thread sums
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) sWarpSum[warp] = incl;
+    __syncthreads();
+    u64 warpBase = 0, blockAgg = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < (int)warp) warpBase += sWarpSum[w];
+        blockAgg += sWarpSum[w];
+    }
+    const u64 threadExcl = warpBase + incl - tsum;
+
+    // publish aggregate, look back (warp 0)
+    if (warp == 0) {
+        if (lane == 0) {
+            tileState[tile] = (tile == 0 ? FLAG_PFX : FLAG_AGG) | blockAgg;
+            __threadfence();
+        }
+        u64 exclusive = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                const int idx = t - (int)lane;
+                u64 st = FLAG_PFX;  // lanes before tile 0 read as "prefix 0"
+                if (idx >= 0) {
+                    do { st = tileState[idx]; } while ((st >> 62) == 0);
+                }
+                const u32 pfxMask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                // nearest tile with an inclusive prefix = lowest lane set in pfxMask
+                const int first = __ffs(pfxMask) - 1;  // always >= 0 eventually (tile 0 or virtual)
+                u64 contrib = ((int)lane <= first || first < 0) ? (st & VALUE_MASK) : 0;
+                if (idx < 0) contrib = 0;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                exclusive += contrib;
+                if (first >= 0) break;
+                t -= 32;
+            }
+            if (lane == 0) {
+                tileState[tile] = FLAG_PFX | (exclusive + blockAgg);
+                __threadfence();
+            }
+        }
+        if (lane == 0) sExclusive = exclusive;
+    }
+    __syncthreads();
+    u64 run = sExclusive + threadExcl;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const u32 idx = base + i;
+        if (idx < n) data[idx] = (u32)run;
+        if (idx == n - 1) sc->nnzC = run;  // 64-bit total: overflow of the u32 API is detectable
+        run += items[i];
+    }
+}
+
+void launch_scan(const LaunchCtx &lc, u32 *data, u32 n, u64 *tileState, Scalars *sc)
+{
+    if (n == 0) return;
+    const u32 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    cudaMemsetAsync(tileState, 0, (size_t)tiles * sizeof(u64), lc.stream);
+    k_scan<<<tiles, SCAN_THREADS, 0, lc.stream>>>(data, n, tileState, sc);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct rows: A row with one entry -> C row = a_ik * B_k, already sorted.
+// (reference: directSpGEMMNumericImplementation, spECK_HashSpGEMM.cuh:543-569)
+// ------------------------------------------------------------------------------------------
+template <typename T, int LPR>
+__global__ void __launch_bounds__(256) k_direct(const u32 *__restrict__ perm, u32 count,
+                                                const u32 *__restrict__ aRp, const u32 *__restrict__ aCi,
+                                                const T *__restrict__ aV, const u32 *__restrict__ bRp,
+                                                const u32 *__restrict__ bCi, const T *__restrict__ bV,
+                                                const u32 *__restrict__ cRp, u32 *__restrict__ cCi,
+                                                T *__restrict__ cV)
+{
+    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const u32 l = threadIdx.x % LPR;
+    if (g >= count) return;
+    const u32 row = perm[g];
+    const u32 a = aRp[row];
+    const u32 k = aCi[a];
+    const T av = aV[a];
+    const u32 bs = bRp[k], len = bRp[k + 1] - bs;
+    const u32 o = cRp[row];
+    for (u32 j = l; j < len; j += LPR) {
+        cCi[o + j] = __ldg(bCi + bs + j);
+        cV[o + j] = av * __ldg(bV + bs + j);
+    }
+}
+
+template <typename T>
+void launch_direct_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
+                           const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *cRp,
+                           u32 *cCi, T *cV)
+{
+    if (count == 0) return;
+    constexpr int LPR = 8;
+    const u32 grid = (u32)(((u64)count * LPR + 255) / 256);
+    k_direct<T, LPR><<<grid, 256, 0, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, cRp, cCi, cV);
+    ++*lc.launches;
+}
+template void launch_direct_numeric<double>(const LaunchCtx &, const u32 *, u32, const u32 *, const u32 *,
+                                            const double *, const u32 *, const u32 *, const double *,
+                                            const u32 *, u32 *, double *);
+template void launch_direct_numeric<float>(const LaunchCtx &, const u32 *, u32, const u32 *, const u32 *,
+                                           const float *, const u32 *, const u32 *, const float *,
+                                           const u32 *, u32 *, float *);
+
+// ------------------------------------------------------------------------------------------
+// Compare (reference source/GPU/Compare.cu:11-62): row lengths, positional column ids,
+// optionally values with a relative tolerance.  One warp per row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_compare(u32 rows, const u32 *__restrict__ rpA,
+                                                 const u32 *__restrict__ ciA, const T *__restrict__ vA,
+                                                 const u32 *__restrict__ rpB, const u32 *__restrict__ ciB,
+                                                 const T *__restrict__ vB, bool compareData, double relTol,
+                                                 Scalars *sc)
+{
+    const u32 row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const u32 a0 = rpA[row], a1 = rpA[row + 1], b0 = rpB[row], b1 = rpB[row + 1];
+    bool bad = (a1 - a0) != (b1 - b0);
+    if (!bad) {
+        for (u32 j = lane; j < a1 - a0; j += 32) {
+            if (ciA[a0 + j] != ciB[b0 + j]) bad = true;
+            if (compareData) {
+                const double x = (double)vA[a0 + j], y = (double)vB[b0 + j];
+                const double d = fabs(x - y), s = fmax(fabs(x), fabs(y));
+                if (d > relTol * s && d > 1e-300) bad = true;
+            }
+        }
+    }
+    if (bad) sc->compareFlag = 1u;
+}
+
+template <typename T>
+void launch_compare(const LaunchCtx &lc, u32 rows, const u32 *rpA, const u32 *ciA, const T *vA, const u32 *rpB,
+                    const u32 *ciB, const T *vB, bool compareData, double relTol, Scalars *sc)
+{
+    if (rows == 0) return;
+    const u32 grid = (u32)(((u64)rows * 32 + 255) / 256);
+    k_compare<T><<<grid, 256, 0, lc.stream>>>(rows, rpA, ciA, vA, rpB, ciB, vB, compareData, relTol, sc);
+    ++*lc.launches;
+}
+template void launch_compare<double>(const LaunchCtx &, u32, const u32 *, const u32 *, const double *,
+                                     const u32 *, const u32 *, const double *, bool, double, Scalars *);
+template void launch_compare<float>(const LaunchCtx &, u32, const u32 *, const u32 *, const float *,
+                                    const u32 *, const u32 *, const float *, bool, double, Scalars *);
+
+}  // namespace sb

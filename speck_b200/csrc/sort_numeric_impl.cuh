@@ -1,0 +1,37 @@
+// speck_b200/csrc/sort_numeric_impl.cuh -- numeric phase of the sort classes for one value type.
+// u32 keys when col_bits + log2(N) <= 32, else u64 keys (wideKeys).
+#pragma once
+#include "sort_rows.cuh"
+
+namespace sb {
+
+template <typename T>
+void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
+                         const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi,
+                         const T *bV, const u32 *rowOps, const u32 *cRp, u32 *cCi, T *cV)
+{
+    if (count == 0) return;
+    u32 *rp = const_cast<u32 *>(cRp);
+#define SB_NUM(G, E)                                                                                         \
+    do {                                                                                                     \
+        if (wideKeys)                                                                                        \
+            launch_sort_rows<G, E, u64, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+        else                                                                                                 \
+            launch_sort_rows<G, E, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+    } while (0)
+    switch (sortClass) {
+        case 0: SB_NUM(4, 1); break;
+        case 1: SB_NUM(8, 1); break;
+        case 2: SB_NUM(16, 1); break;
+        case 3: SB_NUM(32, 1); break;
+        case 4: SB_NUM(32, 2); break;
+        case 5: SB_NUM(32, 4); break;
+        case 6: SB_NUM(32, 8); break;
+        case 7: SB_NUM(32, 16); break;
+        case 8: SB_NUM(32, 32); break;
+        default: break;
+    }
+#undef SB_NUM
+}
+
+}  // namespace sb

@@ -1,0 +1,237 @@
+// speck_b200/csrc/sort_rows.cuh -- "sort" row classes: one lane group (G lanes, E products per
+// lane, N = G*E) per row of C.
+//
+//   gather : the group enumerates the row's products p = 0..ops-1 in (k ascending, B-row order);
+//            consecutive lanes read consecutive entries of a B row (coalesced) and the owner A
+//            entry of each product is found by a shuffle binary search over the inclusive scan
+//            of the B-row lengths (no per-product linear search as in readOperations /
+//            iterateMatrixNumeric of the reference, spECK_HashSpGEMM.cuh:130-215).
+//   sort   : keys (col << IDXBITS | p) are sorted by a bitonic network held in registers
+//            (blocked layout: lane l owns logical elements l*E .. l*E+E-1), shuffles only for
+//            partner distances >= E.  No shared-memory atomics, no hash table, no O(n^2) rank
+//            sort (reference :715-728, :837-850).
+//   emit   : symbolic -> number of distinct columns; numeric -> heads of equal-column runs are
+//            ranked with ballot/popc, the run's products are added in ascending p (= ascending k,
+//            the CPU oracle's order) and (col, val) is written to consecutive positions of C.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int SORT_BLOCK = 128;
+
+template <int N> struct Log2 { static constexpr int value = 1 + Log2<N / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
+template <typename K> __device__ __forceinline__ K key_min(K a, K b) { return a < b ? a : b; }
+template <typename K> __device__ __forceinline__ K key_max(K a, K b) { return a < b ? b : a; }
+
+template <int G, int E, typename KeyT>
+__device__ __forceinline__ void bitonic_sort_regs(KeyT (&reg)[E], const u32 l, const u32 gmask)
+{
+    constexpr int N = G * E;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= E) {
+                const int lm = j / E;  // partner lane distance
+                const bool up = ((l * E) & k) == 0;
+                const bool lower = (l & lm) == 0;
+                const bool keepMin = (up == lower);
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const KeyT o = __shfl_xor_sync(gmask, reg[r], lm, G);
+                    reg[r] = keepMin ? key_min(reg[r], o) : key_max(reg[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & j) == 0) {
+                        const int r2 = r | j;
+                        const bool up = (((l * E + r) & k) == 0);
+                        const KeyT a = reg[r], b = reg[r2];
+                        const KeyT mn = key_min(a, b), mx = key_max(a, b);
+                        reg[r] = up ? mn : mx;
+                        reg[r2] = up ? mx : mn;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int G, int E, typename KeyT, typename T, bool NUMERIC>
+struct SortLayout {
+    static constexpr int N = G * E;
+    static constexpr int NPAD = N + N / 32;            // one pad word per 32: conflict-free blocked write-back
+    static constexpr int GROUPS = SORT_BLOCK / G;      // groups (rows) per block
+    static constexpr size_t KEY_BYTES = (size_t)GROUPS * NPAD * sizeof(KeyT);
+    static constexpr size_t VAL_BYTES = NUMERIC ? (size_t)GROUPS * N * sizeof(T) : 0;
+    static constexpr size_t SMEM = ((KEY_BYTES + 15) / 16) * 16 + VAL_BYTES;
+};
+
+template <int G, int E, typename KeyT, typename T, bool NUMERIC>
+__global__ void __launch_bounds__(SORT_BLOCK)
+k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
+            const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
+            const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
+            u32 *cRp /* symbolic: counts out; numeric: offsets in */, u32 *__restrict__ cCi,
+            T *__restrict__ cV)
+{
+    using L = SortLayout<G, E, KeyT, T, NUMERIC>;
+    constexpr int N = L::N;
+    constexpr int IDXBITS = Log2<N>::value;
+    constexpr KeyT SENT = ~(KeyT)0;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+
+    const u32 laneW = threadIdx.x & 31;
+    const u32 l = threadIdx.x % G;
+    const u32 grp = threadIdx.x / G;
+    const u32 gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (laneW - l));
+    KeyT *keys = reinterpret_cast<KeyT *>(smemRaw) + (size_t)grp * L::NPAD;
+    T *vals = reinterpret_cast<T *>(smemRaw + ((L::KEY_BYTES + 15) / 16) * 16) + (size_t)grp * N;
+
+    const u32 gidx = blockIdx.x * L::GROUPS + grp;
+    const bool active = gidx < count;
+    u32 row = 0, ops = 0, aBeg = 0, aEnd = 0;
+    if (active) {
+        row = perm[gidx];
+        ops = rowOps[row];
+        aBeg = aRp[row];
+        aEnd = aRp[row + 1];
+    }
+
+    // ---------------------------------------------------------------- gather
+    u32 base = 0;
+    for (u32 ab = aBeg; ab < aEnd; ab += G) {
+        const u32 ai = ab + l;
+        u32 bs = 0, len = 0;
+        T av = (T)0;
+        if (ai < aEnd) {
+            const u32 k = __ldg(aCi + ai);
+            bs = __ldg(bRp + k);
+            len = __ldg(bRp + k + 1) - bs;
+            if (NUMERIC) av = __ldg(aV + ai);
+        }
+        u32 incl = len;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const u32 t = __shfl_up_sync(gmask, incl, d, G);
+            if ((int)l >= d) incl += t;
+        }
+        const u32 total = __shfl_sync(gmask, incl, G - 1, G);
+        for (u32 p0 = 0; p0 < total; p0 += G) {
+            const u32 p = p0 + l;
+            u32 lo = 0;
+#pragma unroll
+            for (int s = G / 2; s >= 1; s >>= 1) {
+                const u32 v = __shfl_sync(gmask, incl, lo + s - 1, G);
+                if (v <= p) lo += s;
+            }
+            const u32 oIncl = __shfl_sync(gmask, incl, lo, G);
+            const u32 oLen = __shfl_sync(gmask, len, lo, G);
+            const u32 oBs = __shfl_sync(gmask, bs, lo, G);
+            T oAv = (T)0;
+            if (NUMERIC) oAv = __shfl_sync(gmask, av, lo, G);
+            if (p < total) {
+                const u32 q = oBs + (p - (oIncl - oLen));
+                const u32 col = __ldg(bCi + q);
+                const u32 gp = base + p;
+                if (NUMERIC) {
+                    keys[gp] = ((KeyT)col << IDXBITS) | (KeyT)gp;
+                    vals[gp] = oAv * __ldg(bV + q);
+                } else {
+                    keys[gp] = (KeyT)col;
+                }
+            }
+        }
+        base += total;
+    }
+    __syncwarp(gmask);
+
+    // ---------------------------------------------------------------- sort
+    KeyT reg[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const u32 idx = r * G + l;  // conflict-free striped read; the logical index is l*E + r
+        reg[r] = idx < ops ? keys[idx] : SENT;
+    }
+    __syncwarp(gmask);
+    bitonic_sort_regs<G, E, KeyT>(reg, l, gmask);
+
+    if (!NUMERIC) {
+        // ------------------------------------------------------------ symbolic: distinct columns
+        KeyT prevLast = __shfl_up_sync(gmask, reg[E - 1], 1, G);
+        u32 cnt = 0;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const KeyT prev = (r == 0) ? prevLast : reg[r - 1];
+            const bool valid = reg[r] != SENT;
+            const bool first = (r == 0) && (l == 0);
+            cnt += (valid && (first || reg[r] != prev)) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int d = G / 2; d >= 1; d >>= 1) cnt += __shfl_xor_sync(gmask, cnt, d, G);
+        if (active && l == 0) cRp[row] = cnt;
+        return;
+    } else {
+        // ------------------------------------------------------------ numeric: fold runs, write C
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const u32 idx = l * E + r;
+            keys[idx + (idx >> 5)] = reg[r];
+        }
+        __syncwarp(gmask);
+        const u32 cBase = active ? cRp[row] : 0u;
+        constexpr KeyT IDXMASK = ((KeyT)1 << IDXBITS) - 1;
+        u32 running = 0;
+        for (u32 i0 = 0; i0 < ops; i0 += G) {
+            const u32 i = i0 + l;
+            const bool valid = i < ops;
+            KeyT key = 0;
+            u32 col = 0;
+            bool head = false;
+            if (valid) {
+                key = keys[i + (i >> 5)];
+                col = (u32)(key >> IDXBITS);
+                if (i == 0)
+                    head = true;
+                else {
+                    const KeyT pk = keys[(i - 1) + ((i - 1) >> 5)];
+                    head = (u32)(pk >> IDXBITS) != col;
+                }
+            }
+            const u32 bal = __ballot_sync(gmask, head);
+            const u32 gb = (G == 32) ? bal : ((bal >> (laneW - l)) & ((1u << (G & 31)) - 1u));
+            if (head) {
+                T sum = vals[(u32)(key & IDXMASK)];
+                for (u32 j = i + 1; j < ops; ++j) {
+                    const KeyT k2 = keys[j + (j >> 5)];
+                    if ((u32)(k2 >> IDXBITS) != col) break;
+                    sum = sum + vals[(u32)(k2 & IDXMASK)];
+                }
+                const u32 o = cBase + running + __popc(gb & ((1u << l) - 1u));
+                cCi[o] = col;
+                cV[o] = sum;
+            }
+            running += __popc(gb);
+        }
+    }
+}
+
+template <int G, int E, typename KeyT, typename T, bool NUMERIC>
+void launch_sort_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
+                      const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, u32 *cRp,
+                      u32 *cCi, T *cV)
+{
+    using L = SortLayout<G, E, KeyT, T, NUMERIC>;
+    auto kern = k_sort_rows<G, E, KeyT, T, NUMERIC>;
+    if (L::SMEM > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+    const u32 grid = (count + L::GROUPS - 1) / L::GROUPS;
+    kern<<<grid, SORT_BLOCK, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV);
+    ++*lc.launches;
+}
+
+}  // namespace sb
