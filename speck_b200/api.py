@@ -121,8 +121,19 @@ class DeviceCSR:
     cols = property(lambda self: self.s.cols)
     nnz = property(lambda self: self.s.nnz)
 
+    owned = True
+
+    @classmethod
+    def from_pointers(cls, ctx, rows, cols, nnz, row_offsets_ptr, col_ids_ptr, data_ptr, dtype=np.float64):
+        """Borrowed view over device memory owned by someone else (e.g. torch tensors that
+        received B through an NCCL broadcast)."""
+        d = cls(ctx, dtype)
+        d.s = CsrStruct(rows, cols, nnz, data_ptr, row_offsets_ptr, col_ids_ptr)
+        d.owned = False
+        return d
+
     def free(self):
-        if self.ctx is not None and self.ctx.h:
+        if self.owned and self.ctx is not None and self.ctx.h:
             _check(self.ctx.lib.speck_b200_free_csr(self.ctx.h, ctypes.byref(self.s)))
 
     def view(self, r0=None, r1=None):

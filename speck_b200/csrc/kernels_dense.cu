@@ -6,8 +6,10 @@
 // than the sort classes take.  Differences by design (B200: 227 KB shared memory per CTA):
 //   * the bitmap covers a window of up to 2^20 columns (128 KB) instead of a ~5.8 k-column dense
 //     value window, so most matrices need ONE pass per row instead of range/5.8k passes;
-//   * the bitmap is cleared sparsely: a summary bit per 128-column chunk records which chunks
-//     were touched, so per-row cost is O(products), not O(column range);
+//   * the bitmap is cleared sparsely: a byte per 128-column chunk (plain idempotent stores, no
+//     atomics) records which chunks were touched; only those are counted / cleared;
+//   * the products of a row are enumerated flat over the whole CTA (block scan of the B-row
+//     lengths + binary search), so lanes stay busy whatever the B-row lengths are;
 //   * sorted output comes from popcount ranks (chunk prefix + in-chunk popc), values are
 //     accumulated with fp RED (red.global.add) straight into the zero-initialised C row, so no
 //     value window, no shared-memory CAS loops and no separate sorting pass are needed.
@@ -18,7 +20,7 @@ namespace sb {
 
 constexpr int CHUNK_WORDS = 4;       // 128 columns per chunk = one 16-byte shared load
 constexpr int DENSE_MAX_WIN_BITS = 20;
-constexpr int DENSE_MIN_WIN_BITS = 12;  // 4096 columns = 32 chunks = one summary word
+constexpr int DENSE_MIN_WIN_BITS = 12;  // 4096 columns = 32 chunks
 
 int dense_window_bits(u64 colsB)
 {
@@ -27,12 +29,11 @@ int dense_window_bits(u64 colsB)
     return b;
 }
 
-static size_t dense_smem_bytes(int winBits)
+static size_t dense_smem_bytes(int winBits, int threads, size_t valBytes)
 {
     const size_t words = (size_t)1 << (winBits - 5);
     const size_t chunks = words / CHUNK_WORDS;
-    const size_t sum = chunks / 32 ? chunks / 32 : 1;
-    return (words + chunks + sum) * sizeof(u32);
+    return (words + chunks) * sizeof(u32) + chunks /* touched bytes */ + (size_t)threads * (8 + valBytes);
 }
 
 __device__ __forceinline__ u32 lower_bound_dev(const u32 *__restrict__ a, u32 lo, u32 hi, u32 key)
@@ -71,6 +72,8 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *sWarp, u32 *tota
     return warpBase + incl - v;
 }
 
+// Shared-memory layout of one CTA (u32 words):
+//   bitmap[WWORDS] | chunkPrefix[NCHUNK] | touched[NCHUNK bytes] | sIncl[THREADS] | sBs[THREADS] | sAv[THREADS] (T)
 template <int THREADS, typename T, bool NUMERIC>
 __global__ void __launch_bounds__(THREADS)
 k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, const u32 *__restrict__ aRp,
@@ -82,20 +85,55 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
     const u32 W = 1u << winBits;
     const u32 WWORDS = W >> 5;
     const u32 NCHUNK = WWORDS / CHUNK_WORDS;
-    const u32 NSUM = NCHUNK / 32 ? NCHUNK / 32 : 1;
     u32 *bitmap = dsm;
     u32 *chunkPrefix = bitmap + WWORDS;
-    u32 *summary = chunkPrefix + NCHUNK;
+    unsigned char *touched = reinterpret_cast<unsigned char *>(chunkPrefix + NCHUNK);
+    u32 *sIncl = reinterpret_cast<u32 *>(touched + NCHUNK);
+    u32 *sBs = sIncl + THREADS;
+    T *sAv = reinterpret_cast<T *>(sBs + THREADS);
     __shared__ u32 sWarp[32];
     __shared__ u32 sRow, sMin, sMax;
 
     const u32 tid = threadIdx.x;
     for (u32 i = tid; i < WWORDS; i += THREADS) bitmap[i] = 0;
-    for (u32 i = tid; i < NSUM; i += THREADS) summary[i] = 0;
+    for (u32 i = tid; i < NCHUNK / 4; i += THREADS) reinterpret_cast<u32 *>(touched)[i] = 0;
     const u32 numWin = (colsB + W - 1) >> winBits;
     const u32 CPT = (NCHUNK + THREADS - 1) / THREADS;  // consecutive chunks per thread
     const u32 chBeg = tid * CPT;
     const u32 chEnd = min(NCHUNK, chBeg + CPT);
+
+    // one batch = up to THREADS entries of the A row: B-row bounds trimmed to the window, inclusive
+    // scan of the lengths; products of the batch are then enumerated flat (p -> owner by binary
+    // search), so every thread gets the same number of products whatever the B-row lengths are.
+    auto load_batch = [&](u32 ab, u32 aEnd, u32 winLo, u32 winHi, u32 &nb) -> u32 {
+        nb = min((u32)THREADS, aEnd - ab);
+        u32 bs = 0, len = 0;
+        if (tid < nb) {
+            const u32 k = __ldg(aCi + ab + tid);
+            bs = __ldg(bRp + k);
+            u32 be = __ldg(bRp + k + 1);
+            if (numWin > 1) {
+                bs = lower_bound_dev(bCi, bs, be, winLo);
+                be = lower_bound_dev(bCi, bs, be, winHi);
+            }
+            len = be - bs;
+            if (NUMERIC) sAv[tid] = __ldg(aV + ab + tid);
+        }
+        u32 total;
+        const u32 excl = block_exclusive_scan<THREADS>(len, sWarp, &total);
+        sIncl[tid] = excl + len;
+        sBs[tid] = bs - excl;  // q = sBs[owner] + p
+        __syncthreads();
+        return total;
+    };
+    auto owner_of = [&](u32 p, u32 nb) -> u32 {
+        u32 lo = 0, hi = nb;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (sIncl[mid] <= p) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
 
     while (true) {
         __syncthreads();
@@ -105,14 +143,7 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
         if (ri >= count) break;
         const u32 row = perm[ri];
         const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
-        const u32 ops = rowOps[row];
-        // lanes per B row: largest power of two <= average B-row length, in [4, 32]
-        const u32 avg = ops / (aEnd - aBeg);
-        int shift = 5;
-        while (shift > 2 && (1u << shift) > avg) --shift;
-        const u32 LPR = 1u << shift;
-        const u32 groups = THREADS >> shift;
-        const u32 g = tid >> shift, gl = tid & (LPR - 1);
+        const bool oneBatch = (aEnd - aBeg) <= (u32)THREADS;
 
         u32 winFirst = 0, winLast = 0;
         if (numWin > 1) {  // column extent of the row -> windows to visit
@@ -138,71 +169,50 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
         for (u32 win = winFirst; win <= winLast; ++win) {
             const u32 winLo = win << winBits;
             const u32 winHi = min(colsB, winLo + W);
+            u32 nb = 0, total = 0;
             // ------------------------------------------------ pass A: set column bits
-            for (u32 a = aBeg + g; a < aEnd; a += groups) {
-                const u32 k = __ldg(aCi + a);
-                u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
-                if (numWin > 1) {
-                    bs = lower_bound_dev(bCi, bs, be, winLo);
-                    be = lower_bound_dev(bCi, bs, be, winHi);
+            for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
+                total = load_batch(ab, aEnd, winLo, winHi, nb);
+                for (u32 p = tid; p < total; p += THREADS) {
+                    const u32 o = owner_of(p, nb);
+                    const u32 c = __ldg(bCi + sBs[o] + p) - winLo;
+                    atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+                    touched[c >> 7] = 1;
                 }
-                for (u32 q = bs + gl; q < be; q += LPR) {
-                    const u32 c = __ldg(bCi + q) - winLo;
-                    const u32 w = c >> 5;
-                    const u32 old = atomicOr(&bitmap[w], 1u << (c & 31));
-                    if (old == 0) atomicOr(&summary[w >> 7], 1u << ((w >> 2) & 31));
-                }
+                __syncthreads();
             }
-            __syncthreads();
             // ------------------------------------------------ chunk counts (touched chunks only)
             u32 tsum = 0;
             for (u32 ch = chBeg; ch < chEnd; ++ch) {
-                if ((summary[ch >> 5] >> (ch & 31)) & 1u) {
+                if (touched[ch]) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(&bitmap[ch * CHUNK_WORDS]);
                     if (NUMERIC) chunkPrefix[ch] = tsum;
                     tsum += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                    if (!NUMERIC) {  // symbolic: this thread is the only reader left -> clear now
+                        *reinterpret_cast<uint4 *>(&bitmap[ch * CHUNK_WORDS]) = make_uint4(0, 0, 0, 0);
+                        touched[ch] = 0;
+                    }
                 }
             }
             u32 winTotal;
             const u32 texcl = block_exclusive_scan<THREADS>(tsum, sWarp, &winTotal);
 
             if (NUMERIC) {
-                // -------------------------------------------- final prefixes + sorted column ids
-                for (u32 ch = chBeg; ch < chEnd; ++ch) {
-                    if ((summary[ch >> 5] >> (ch & 31)) & 1u) {
-                        const u32 pfx = chunkPrefix[ch] + texcl + winBase;
-                        chunkPrefix[ch] = pfx;
-                        u32 pos = rowStart + pfx;
-                        const uint4 v = *reinterpret_cast<const uint4 *>(&bitmap[ch * CHUNK_WORDS]);
-                        const u32 wv[4] = {v.x, v.y, v.z, v.w};
-                        const u32 colBase = winLo + ch * (CHUNK_WORDS * 32);
-#pragma unroll
-                        for (int wi = 0; wi < 4; ++wi) {
-                            u32 bits = wv[wi];
-                            while (bits) {
-                                const u32 b = __ffs(bits) - 1;
-                                bits &= bits - 1;
-                                cCi[pos++] = colBase + wi * 32 + b;
-                            }
-                        }
-                    }
-                }
-                // -------------------------------------------- zero the value slots of this window
+                for (u32 ch = chBeg; ch < chEnd; ++ch)
+                    if (touched[ch]) chunkPrefix[ch] += texcl + winBase;
+                // zero the value slots of this window; pass B adds into them with RED
                 for (u32 j = tid; j < winTotal; j += THREADS) cV[rowStart + winBase + j] = (T)0;
                 __threadfence_block();
                 __syncthreads();
-                // -------------------------------------------- pass B: rank + RED
-                for (u32 a = aBeg + g; a < aEnd; a += groups) {
-                    const u32 k = __ldg(aCi + a);
-                    const T av = __ldg(aV + a);
-                    u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
-                    if (numWin > 1) {
-                        bs = lower_bound_dev(bCi, bs, be, winLo);
-                        be = lower_bound_dev(bCi, bs, be, winHi);
-                    }
-                    for (u32 q = bs + gl; q < be; q += LPR) {
-                        const u32 c = __ldg(bCi + q) - winLo;
-                        const T prod = av * __ldg(bV + q);
+                // -------------------------------------------- pass B: rank -> column id + RED of the product
+                for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
+                    if (!oneBatch) total = load_batch(ab, aEnd, winLo, winHi, nb);
+                    for (u32 p = tid; p < total; p += THREADS) {
+                        const u32 o = owner_of(p, nb);
+                        const u32 q = sBs[o] + p;
+                        const u32 col = __ldg(bCi + q);
+                        const T prod = sAv[o] * __ldg(bV + q);
+                        const u32 c = col - winLo;
                         const u32 w = c >> 5;
                         const u32 ch = w >> 2;
                         const u32 wi = w & 3;
@@ -210,19 +220,20 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                         const u32 below = (wi > 0 ? __popc(v.x) : 0) + (wi > 1 ? __popc(v.y) : 0) +
                                           (wi > 2 ? __popc(v.z) : 0);
                         const u32 word = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
-                        const u32 rank = chunkPrefix[ch] + below + __popc(word & ((1u << (c & 31)) - 1u));
-                        atomicAdd(&cV[rowStart + rank], prod);
+                        const u32 pos = rowStart + chunkPrefix[ch] + below + __popc(word & ((1u << (c & 31)) - 1u));
+                        cCi[pos] = col;  // every product of a column writes the same value
+                        atomicAdd(&cV[pos], prod);
+                    }
+                    __syncthreads();
+                }
+                // -------------------------------------------- sparse clear
+                for (u32 ch = chBeg; ch < chEnd; ++ch) {
+                    if (touched[ch]) {
+                        *reinterpret_cast<uint4 *>(&bitmap[ch * CHUNK_WORDS]) = make_uint4(0, 0, 0, 0);
+                        touched[ch] = 0;
                     }
                 }
-                __syncthreads();
             }
-            // ------------------------------------------------ sparse clear
-            for (u32 ch = chBeg; ch < chEnd; ++ch) {
-                if ((summary[ch >> 5] >> (ch & 31)) & 1u)
-                    *reinterpret_cast<uint4 *>(&bitmap[ch * CHUNK_WORDS]) = make_uint4(0, 0, 0, 0);
-            }
-            __syncthreads();
-            for (u32 i = tid; i < NSUM; i += THREADS) summary[i] = 0;
             __syncthreads();
             winBase += winTotal;
         }
@@ -236,7 +247,7 @@ static void launch_dense_t(const LaunchCtx &lc, const u32 *perm, u32 count, u32 
                            const u32 *rowOps, u32 *cRp, u32 *cCi, T *cV)
 {
     const int winBits = dense_window_bits(colsB);
-    const size_t smem = dense_smem_bytes(winBits);
+    const size_t smem = dense_smem_bytes(winBits, THREADS, sizeof(T));
     auto kern = k_dense_rows<THREADS, T, NUMERIC>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int perSm = 1;

@@ -26,34 +26,60 @@ template <> struct Log2<1> { static constexpr int value = 0; };
 template <typename K> __device__ __forceinline__ K key_min(K a, K b) { return a < b ? a : b; }
 template <typename K> __device__ __forceinline__ K key_max(K a, K b) { return a < b ? b : a; }
 
+// Ascending bitonic sort of N = G*E keys, blocked layout (logical index = l*E + r).
+// "Mirrored" formulation: each merge of width k starts with partner = idx ^ (k-1), followed by
+// half-cleaners partner = idx ^ j (j = k/4 .. 1).  Every compare-exchange is ascending (lower index
+// keeps the minimum), so no direction selects are needed: 2 min/max per intra-lane exchange, one
+// shuffle + one predicated min/max per inter-lane exchange.
 template <int G, int E, typename KeyT>
 __device__ __forceinline__ void bitonic_sort_regs(KeyT (&reg)[E], const u32 l, const u32 gmask)
 {
     constexpr int N = G * E;
 #pragma unroll
     for (int k = 2; k <= N; k <<= 1) {
+        // ---- mirrored stage
+        if (k <= E) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int r = 0; r < E; ++r) {
+                const int r2 = r ^ (k - 1);
+                if (r < r2) {
+                    const KeyT a = reg[r], b = reg[r2];
+                    reg[r] = key_min(a, b);
+                    reg[r2] = key_max(a, b);
+                }
+            }
+        } else {
+            const int lm = k / E - 1;                 // partner lane = l ^ lm, partner register = E-1-r
+            const bool lower = (l & (k / (2 * E))) == 0;
+#pragma unroll
+            for (int r = 0; r < (E + 1) / 2; ++r) {
+                const int r2 = E - 1 - r;
+                const KeyT o1 = __shfl_xor_sync(gmask, reg[r2], lm, G);
+                if (r2 != r) {
+                    const KeyT o2 = __shfl_xor_sync(gmask, reg[r], lm, G);
+                    reg[r2] = lower ? key_min(reg[r2], o2) : key_max(reg[r2], o2);
+                }
+                reg[r] = lower ? key_min(reg[r], o1) : key_max(reg[r], o1);
+            }
+        }
+        // ---- half cleaners
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
             if (j >= E) {
-                const int lm = j / E;  // partner lane distance
-                const bool up = ((l * E) & k) == 0;
+                const int lm = j / E;
                 const bool lower = (l & lm) == 0;
-                const bool keepMin = (up == lower);
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
                     const KeyT o = __shfl_xor_sync(gmask, reg[r], lm, G);
-                    reg[r] = keepMin ? key_min(reg[r], o) : key_max(reg[r], o);
+                    reg[r] = lower ? key_min(reg[r], o) : key_max(reg[r], o);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
                     if ((r & j) == 0) {
-                        const int r2 = r | j;
-                        const bool up = (((l * E + r) & k) == 0);
-                        const KeyT a = reg[r], b = reg[r2];
-                        const KeyT mn = key_min(a, b), mx = key_max(a, b);
-                        reg[r] = up ? mn : mx;
-                        reg[r2] = up ? mx : mn;
+                        const KeyT a = reg[r], b = reg[r | j];
+                        reg[r] = key_min(a, b);
+                        reg[r | j] = key_max(a, b);
                     }
                 }
             }
