@@ -63,7 +63,7 @@ typedef struct speck_timings {
         complete;
 } speck_timings;
 
-#define SPECK_NUM_CLASSES 12
+#define SPECK_NUM_CLASSES 16
 
 /* What the last multiply did (for bench.py's roofline arithmetic and the tests). */
 typedef struct speck_stats {
@@ -89,7 +89,7 @@ int speck_b200_sm_count(const speck_ctx *ctx);
 /* C = A . B on the context's device.  A and B are borrowed device views.  C is in/out with
  * the reference's ownership rules (source/GPU/Multiply.cu:155-165, 589-592):
  *   - if C->rows == A->rows and C->row_offsets != NULL the row_offsets buffer is reused,
- *     otherwise a new one is cudaMalloc'ed (the old one is NOT freed, as in the reference);
+ *     otherwise the old one is cudaFree'd and a new one cudaMalloc'ed;
  *   - if C->nnz != nnz(C) (or data/col_ids are NULL) data and col_ids are cudaFree'd and
  *     re-allocated with cudaMalloc, so the caller's dCSR destructor can cudaFree them;
  *   - A->nnz == 0 or B->nnz == 0: only C->nnz = 0 is written (Multiply.cu:67-70);
@@ -133,7 +133,7 @@ int speck_b200_synchronize(speck_ctx *ctx);
 void *speck_b200_stream(speck_ctx *ctx);
 
 /* Tuning knobs (integers): "sort_max" = largest row-product count handled by the register-sort
- * classes (power of two in [4, 1024]; rows with more products take the bitmap path);
+ * classes (power of two in [4, 8192]; rows with more products take the bitmap path);
  * "release_workspace" = 1 frees the pooled workspace now. */
 int speck_b200_set_option(speck_ctx *ctx, const char *key, long long value);
 

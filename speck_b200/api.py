@@ -20,9 +20,9 @@ from .matrices import HostCSR
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libspeck_b200.so")
 
-NUM_CLASSES = 12
+NUM_CLASSES = 16
 BIN_NAMES = ["direct", "sort4", "sort8", "sort16", "sort32", "sort64", "sort128", "sort256",
-             "sort512", "sort1024", "dense"]
+             "sort512", "sort1024", "sort2048", "sort4096", "sort8192", "dense"]
 
 
 class SpeckError(RuntimeError):

@@ -6,8 +6,9 @@
 // Row classes ("bins"):
 //   BIN_DIRECT        A row has exactly one entry: C row = scaled copy of one B row
 //                     (reference: directSpGEMM*, spECK_HashSpGEMM.cuh:543-589)
-//   BIN_SORT0 + c     products <= 4<<c (c = 0..8): register bitonic sort of the row's
-//                     products by a lane group, duplicates folded after the sort
+//   BIN_SORT0 + c     products <= 4<<c (c = 0..11): register bitonic sort of the row's
+//                     products by a lane group (c <= 8) or a CTA of 2/4/8 warps (c = 9..11),
+//                     duplicates folded after the sort
 //                     (replaces the smem hash + O(n^2) rank sort, :591-866)
 //   BIN_DENSE         more products: CTA per row, sparse-cleared column bitmap in
 //                     shared memory, popcount ranks give the sorted position of every
@@ -22,12 +23,13 @@ typedef uint64_t u64;
 
 namespace sb {
 
-constexpr int NUM_SORT = 9;                 // sort classes: 4, 8, ..., 1024 products
+constexpr int NUM_SORT = 12;                // sort classes: 4, 8, ..., 1024 (one lane group) and 2048, 4096, 8192 (one CTA)
+constexpr int NUM_WARP_SORT = 9;
 constexpr int BIN_DIRECT = 0;
 constexpr int BIN_SORT0 = 1;
-constexpr int BIN_DENSE = BIN_SORT0 + NUM_SORT;   // 10
-constexpr int NUM_BINS = BIN_DENSE + 1;           // 11
-constexpr u32 SORT_MAX_PRODUCTS = 4u << (NUM_SORT - 1);  // 1024
+constexpr int BIN_DENSE = BIN_SORT0 + NUM_SORT;   // 13
+constexpr int NUM_BINS = BIN_DENSE + 1;           // 14
+constexpr u32 SORT_MAX_PRODUCTS = 4u << (NUM_SORT - 1);  // 8192
 
 // Device-resident scalars of one multiply; mirrored into pinned host memory.
 struct Scalars {

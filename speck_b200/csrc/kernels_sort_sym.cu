@@ -1,5 +1,5 @@
 // speck_b200/csrc/kernels_sort_sym.cu -- symbolic phase of the sort classes (u32 column keys).
-#include "sort_rows.cuh"
+#include "sort_cta.cuh"
 
 namespace sb {
 
@@ -20,6 +20,9 @@ void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, const u32 *perm, u
         case 6: SB_SYM(32, 8); break;
         case 7: SB_SYM(32, 16); break;
         case 8: SB_SYM(32, 32); break;
+        case 9: launch_sort_rows_cta<2, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
+        case 10: launch_sort_rows_cta<4, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
+        case 11: launch_sort_rows_cta<8, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
         default: break;
     }
 #undef SB_SYM

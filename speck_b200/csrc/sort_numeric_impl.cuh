@@ -1,7 +1,7 @@
 // speck_b200/csrc/sort_numeric_impl.cuh -- numeric phase of the sort classes for one value type.
 // u32 keys when col_bits + log2(N) <= 32, else u64 keys (wideKeys).
 #pragma once
-#include "sort_rows.cuh"
+#include "sort_cta.cuh"
 
 namespace sb {
 
@@ -19,6 +19,13 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
         else                                                                                                 \
             launch_sort_rows<G, E, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
     } while (0)
+#define SB_NUM_CTA(W)                                                                                        \
+    do {                                                                                                     \
+        if (wideKeys)                                                                                        \
+            launch_sort_rows_cta<W, u64, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+        else                                                                                                 \
+            launch_sort_rows_cta<W, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+    } while (0)
     switch (sortClass) {
         case 0: SB_NUM(4, 1); break;
         case 1: SB_NUM(8, 1); break;
@@ -29,9 +36,13 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
         case 6: SB_NUM(32, 8); break;
         case 7: SB_NUM(32, 16); break;
         case 8: SB_NUM(32, 32); break;
+        case 9: SB_NUM_CTA(2); break;
+        case 10: SB_NUM_CTA(4); break;
+        case 11: SB_NUM_CTA(8); break;
         default: break;
     }
 #undef SB_NUM
+#undef SB_NUM_CTA
 }
 
 }  // namespace sb

@@ -26,6 +26,34 @@ template <> struct Log2<1> { static constexpr int value = 0; };
 template <typename K> __device__ __forceinline__ K key_min(K a, K b) { return a < b ? a : b; }
 template <typename K> __device__ __forceinline__ K key_max(K a, K b) { return a < b ? b : a; }
 
+// half-cleaner stages j = jStart, jStart/2, ..., 1 (partner = idx ^ j, ascending)
+template <int G, int E, typename KeyT>
+__device__ __forceinline__ void bitonic_half_cleaners(KeyT (&reg)[E], const u32 l, const u32 gmask, const int jStart)
+{
+#pragma unroll
+    for (int j = (G * E) >> 1; j > 0; j >>= 1) {
+        if (j > jStart) continue;  // resolved at compile time once the caller's loop is unrolled
+        if (j >= E) {
+            const int lm = j / E;
+            const bool lower = (l & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const KeyT o = __shfl_xor_sync(gmask, reg[r], lm, G);
+                reg[r] = lower ? key_min(reg[r], o) : key_max(reg[r], o);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                if ((r & j) == 0) {
+                    const KeyT a = reg[r], b = reg[r | j];
+                    reg[r] = key_min(a, b);
+                    reg[r | j] = key_max(a, b);
+                }
+            }
+        }
+    }
+}
+
 // Ascending bitonic sort of N = G*E keys, blocked layout (logical index = l*E + r).
 // "Mirrored" formulation: each merge of width k starts with partner = idx ^ (k-1), followed by
 // half-cleaners partner = idx ^ j (j = k/4 .. 1).  Every compare-exchange is ascending (lower index
@@ -63,27 +91,7 @@ __device__ __forceinline__ void bitonic_sort_regs(KeyT (&reg)[E], const u32 l, c
             }
         }
         // ---- half cleaners
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            if (j >= E) {
-                const int lm = j / E;
-                const bool lower = (l & lm) == 0;
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const KeyT o = __shfl_xor_sync(gmask, reg[r], lm, G);
-                    reg[r] = lower ? key_min(reg[r], o) : key_max(reg[r], o);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    if ((r & j) == 0) {
-                        const KeyT a = reg[r], b = reg[r | j];
-                        reg[r] = key_min(a, b);
-                        reg[r | j] = key_max(a, b);
-                    }
-                }
-            }
-        }
+        bitonic_half_cleaners<G, E, KeyT>(reg, l, gmask, k >> 2);
     }
 }
 

@@ -21,11 +21,23 @@ def test_uniform_random(ctx, n, d, seed):
     check_case(ctx, M.uniform_random(n, n, d, seed), what=f"uniform {n} {d}")
 
 
+@pytest.fixture(params=[8192, 1024, 64])
+def sort_max(ctx, request):
+    """Run a case with the sort/bitmap switch at several places so that every row class
+    (lane-group sort, CTA sort, bitmap) sees the same inputs."""
+    ctx.set_option("sort_max", request.param)
+    yield request.param
+    ctx.set_option("sort_max", 8192)
+
+
 @pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16), (15, 16)])
-def test_rmat(ctx, scale, ef):
+def test_rmat(ctx, sort_max, scale, ef):
     A = M.rmat(scale, ef, seed=scale)
-    got, st = check_case(ctx, A, what=f"rmat{scale}")
-    assert st["class_rows"]["dense"] > 0 or scale < 13
+    got, st = check_case(ctx, A, what=f"rmat{scale} sort_max={sort_max}")
+    if sort_max <= 1024 and scale >= 13:
+        assert st["class_rows"]["dense"] > 0
+    if sort_max == 8192 and scale >= 15:
+        assert st["class_rows"]["sort2048"] > 0 and st["class_rows"]["sort4096"] > 0
 
 
 def test_rectangular(ctx):
@@ -38,7 +50,7 @@ def _rows_with_products(targets, cols=4096, seed=0):
     """A whose row i has exactly targets[i] products against a B with one entry... B row k has
     length k+1 (k < 64) so any product count can be composed; all columns distinct mod cols."""
     rng = np.random.default_rng(seed)
-    nb = 64
+    nb = 128
     # B: row k has k+1 random distinct columns
     br, bc = [], []
     for k in range(nb):
@@ -50,7 +62,7 @@ def _rows_with_products(targets, cols=4096, seed=0):
     for i, t in enumerate(targets):
         left = t
         used = set()
-        # greedy: use long rows first, each B row at most once per A row -> products <= 2080
+        # greedy: use long rows first, each B row at most once per A row -> products <= 8256
         for k in range(nb - 1, -1, -1):
             if left >= k + 1 and k not in used:
                 ar.append(i), ac.append(k)
@@ -64,14 +76,15 @@ def _rows_with_products(targets, cols=4096, seed=0):
 def test_class_boundaries(ctx):
     """product counts straddling every class boundary (4<<c) and the sort/dense switch."""
     targets = []
-    for c in range(0, 10):
+    for c in range(0, 12):
         b = 4 << c
         targets += [b - 1, b, b + 1]
-    targets += [1, 2, 3, 2047, 2080]
-    A, B = _rows_with_products(targets)
+    targets += [1, 2, 3, 8255, 8256]
+    A, B = _rows_with_products(targets, cols=16384)
     got, st = check_case(ctx, A, B, what="class boundaries")
     assert st["class_rows"]["dense"] >= 3
-    assert st["class_rows"]["sort1024"] >= 1
+    for name in ("sort1024", "sort2048", "sort4096", "sort8192"):
+        assert st["class_rows"][name] >= 3, name
 
 
 def test_empty_rows_and_empty_b_rows(ctx):
@@ -131,13 +144,13 @@ def test_empty_products_conventions(ctx):
     assert got.nnz == 0 and got.rows == 3
 
 
-def test_banded_high_compression_dense_path(ctx):
+def test_banded_high_compression(ctx, sort_max):
     A = M.banded_fem_like(n=3000, per_row=64, clusters=8, band=300, seed=41)
-    got, st = check_case(ctx, A, what="banded")
-    assert st["class_rows"]["dense"] > 0
+    got, st = check_case(ctx, A, what=f"banded sort_max={sort_max}")
+    assert (st["class_rows"]["dense"] > 0) == (sort_max < 4096)
 
 
-def test_wide_matrix_multiwindow_and_wide_keys(ctx):
+def test_wide_matrix_multiwindow_and_wide_keys(ctx, sort_max):
     """cols > 2^20 -> several bitmap windows in the dense path; cols*N > 2^32 -> u64 sort keys."""
     rng = np.random.default_rng(21)
     n, cols = 3000, (1 << 23) + 12345
@@ -150,8 +163,9 @@ def test_wide_matrix_multiwindow_and_wide_keys(ctx):
     A = M.from_coo(n, n, np.concatenate([r, hub_r]), np.concatenate([c, hub_c]), seed=22)
     mb = 60000
     B = M.from_coo(n, cols, rng.integers(0, n, mb), rng.integers(0, cols, mb), seed=23)
-    got, st = check_case(ctx, A, B, what="wide")
-    assert st["class_rows"]["dense"] >= 4
+    got, st = check_case(ctx, A, B, what=f"wide sort_max={sort_max}")
+    if sort_max <= 1024:
+        assert st["class_rows"]["dense"] >= 4
 
 
 def test_fp32(ctx):
@@ -209,4 +223,4 @@ def test_sort_max_option_routes_more_rows_to_dense(ctx):
         got, st = check_case(ctx, A, what="sort_max=64")
         assert st["class_rows"]["sort128"] == 0 and st["class_rows"]["dense"] > 0
     finally:
-        ctx.set_option("sort_max", 1024)
+        ctx.set_option("sort_max", 8192)
