@@ -131,6 +131,10 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     const T *aV = (const T *)A->data, *bV = (const T *)B->data;
     c->launches = 0;
     LaunchCtx lc{c->main, c->smCount, &c->launches};
+    // CTA-level sort classes (> 1024 products) are used only while (col << log2 N) fits a u32 key;
+    // wider matrices send those rows to the bitmap path instead of sorting u64 keys.
+    u32 sortMax = c->sortMax;
+    while (sortMax > 1024 && ((u64)colsB * sortMax) > (1ull << 32)) sortMax >>= 1;
 
     // ---- init: workspace, C.row_offsets (reuse rule of Multiply.cu:155-165)
     cudaEventRecord(c->evStage[0], c->main);
@@ -150,8 +154,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
 
     // ---- analysis + binning
-    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, rowOps, cRp, c->dSc, c->sortMax);
-    launch_bin_scatter(lc, rows, aRp, rowOps, perm, c->dSc, c->sortMax);
+    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, rowOps, cRp, c->dSc, sortMax);
+    launch_bin_scatter(lc, rows, aRp, rowOps, perm, c->dSc, sortMax);
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     cudaEventRecord(c->evStage[1], c->main);
     CU_TRY(cudaStreamSynchronize(c->main));
