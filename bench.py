@@ -53,6 +53,8 @@ def load_workload(name, seed):
     elif name == "webbase_like":
         A = M.webbase_like(seed=seed)
     elif name == "cant_like":
+        A = M.fem3d_like(seed=seed)
+    elif name == "banded_like":
         A = M.banded_fem_like(seed=seed)
     elif name == "econ_like":
         A = M.econ_like(seed=seed)

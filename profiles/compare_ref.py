@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workloads", nargs="*", default=["econ_like", "circuit_like", "webbase_like", "cant_like", "rmat20"])
+    ap.add_argument("workloads", nargs="*", default=["econ_like", "circuit_like", "webbase_like", "cant_like", "banded_like", "rmat20"])
     ap.add_argument("--out", default="gpurun_out/compare.jsonl")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=10)
@@ -31,8 +31,8 @@ def main():
     ctx = api.Context(0)
     with open(args.out, "a") as fo:
         for w in args.workloads:
-            A = load_workload(w, 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 41, "econ_like": 42, "circuit_like": 43}[w])
-            seed = 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 41, "econ_like": 42, "circuit_like": 43}[w]
+            A = load_workload(w, 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w])
+            seed = 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w]
             dA = ctx.upload(A)
             dC = api.DeviceCSR(ctx)
             for _ in range(args.warmup):

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libspeck_b200.so")
 
 NUM_CLASSES = 16
 BIN_NAMES = ["direct", "sort4", "sort8", "sort16", "sort32", "sort64", "sort128", "sort256",
-             "sort512", "sort1024", "sort2048", "sort4096", "sort8192", "dense"]
+             "sort512", "sort1024", "sort2048", "sort4096", "sort8192", "dense_local", "dense"]
 
 
 class SpeckError(RuntimeError):

@@ -59,7 +59,7 @@ struct speck_ctx {
     cudaEvent_t evStage[6] = {};
     Scalars *dSc = nullptr;
     Scalars *hSc = nullptr;  // pinned
-    DevBuf rowOps, perm, tileState;
+    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore;
     DevBuf stage[6];          // device staging of the *_host entry points (A: rp, ci, v; B: rp, ci, v)
     void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
     size_t hostOutCap[3] = {};
@@ -141,6 +141,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     int rc;
     if ((rc = ensure(c->rowOps, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->perm, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->rowMin, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->rowMax, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->tileState, scan_tile_state_bytes(rows + 1)))) return rc;
     u32 *cRp = C->row_offsets;
     if (!(C->rows == A->rows && cRp != nullptr)) {
@@ -151,11 +153,12 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         C->rows = A->rows;
     }
     u32 *rowOps = (u32 *)c->rowOps.p, *perm = (u32 *)c->perm.p;
+    u32 *rowMin = (u32 *)c->rowMin.p, *rowMax = (u32 *)c->rowMax.p;
     CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
 
     // ---- analysis + binning
-    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, rowOps, cRp, c->dSc, sortMax);
-    launch_bin_scatter(lc, rows, aRp, rowOps, perm, c->dSc, sortMax);
+    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax);
+    launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax);
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     cudaEventRecord(c->evStage[1], c->main);
     CU_TRY(cudaStreamSynchronize(c->main));
@@ -173,13 +176,21 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     binStart[0] = 0;
     for (int b = 0; b < NUM_BINS; ++b) binStart[b + 1] = binStart[b] + s1.binCount[b];
 
+    // bitmaps of the local-dense rows are kept from the symbolic to the numeric phase (2 KB per row)
+    u32 *bitmapStore = nullptr;
+    {
+        const size_t need = dense_local_store_bytes(s1.binCount[BIN_DENSE_LOCAL]);
+        if (need && need <= ((size_t)8 << 30) && ensure(c->bitmapStore, need) == SPECK_OK) bitmapStore = (u32 *)c->bitmapStore.p;
+    }
     // ---- symbolic: dense rows first (longest), then the sort classes from large to small
     fork_streams(c);
     int sidx = 0;
-    {
+    for (int loc = 0; loc < 2; ++loc) {
+        const int bin = loc ? BIN_DENSE_LOCAL : BIN_DENSE;
+        if (!s1.binCount[bin]) continue;
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        launch_dense_symbolic(ls, perm + binStart[BIN_DENSE], s1.binCount[BIN_DENSE], &c->dSc->denseCounter[0], aRp,
-                              aCi, bRp, bCi, colsB, rowOps, cRp);
+        launch_dense_symbolic(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[loc], aRp,
+                              aCi, bRp, bCi, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp);
     }
     for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
@@ -223,10 +234,12 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     cudaEventRecord(c->evStage[4], c->main);
     fork_streams(c);
     sidx = 0;
-    {
+    for (int loc = 0; loc < 2; ++loc) {
+        const int bin = loc ? BIN_DENSE_LOCAL : BIN_DENSE;
+        if (!s1.binCount[bin]) continue;
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        launch_dense_numeric<T>(ls, perm + binStart[BIN_DENSE], s1.binCount[BIN_DENSE], &c->dSc->denseCounter[1], aRp,
-                                aCi, aV, bRp, bCi, bV, colsB, rowOps, cRp, cCi, cV);
+        launch_dense_numeric<T>(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[2 + loc],
+                                aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV);
     }
     for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
@@ -259,7 +272,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     cudaEventElapsedTime(&st.ms_scan, c->evStage[2], c->evStage[3]);
     cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
     cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
-    st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->tileState.cap;
+    st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->rowMin.cap + c->rowMax.cap + c->tileState.cap + c->bitmapStore.cap;
     if (tm) {
         float allocMs = 0.f;
         cudaEventElapsedTime(&allocMs, c->evStage[3], c->evStage[4]);
@@ -409,7 +422,7 @@ int speck_b200_destroy(speck_ctx *c)
     if (!c) return SPECK_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    release(c->rowOps); release(c->perm); release(c->tileState);
+    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore);
     for (auto &b : c->stage) release(b);
     for (auto &h : c->hostOut) if (h) cudaFreeHost(h);
     if (c->hostC.data) cudaFree(c->hostC.data);
@@ -469,11 +482,13 @@ int speck_b200_row_products(speck_ctx *c, const speck_csr *A, const speck_csr *B
     int rc;
     if ((rc = ensure(c->rowOps, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->perm, (size_t)rows * 4))) return rc;  // scratch for the rowNnz side output
+    if ((rc = ensure(c->rowMin, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->rowMax, (size_t)rows * 4))) return rc;
     CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
     u32 n = 0;
     LaunchCtx lc{c->main, c->smCount, &n};
-    launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, (u32 *)c->rowOps.p, (u32 *)c->perm.p,
-                   c->dSc, c->sortMax);
+    launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, B->col_ids, (u32 *)c->rowOps.p,
+                   (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax);
     if (dRowOps) CU_TRY(cudaMemcpyAsync(dRowOps, c->rowOps.p, (size_t)rows * 4, cudaMemcpyDeviceToDevice, c->main));
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     CU_TRY(cudaStreamSynchronize(c->main));
@@ -554,7 +569,7 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "release_workspace")) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        release(c->rowOps); release(c->perm); release(c->tileState);
+        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore);
         for (auto &b : c->stage) release(b);
         return SPECK_OK;
     }

@@ -27,8 +27,11 @@ constexpr int NUM_SORT = 12;                // sort classes: 4, 8, ..., 1024 (on
 constexpr int NUM_WARP_SORT = 9;
 constexpr int BIN_DIRECT = 0;
 constexpr int BIN_SORT0 = 1;
-constexpr int BIN_DENSE = BIN_SORT0 + NUM_SORT;   // 13
-constexpr int NUM_BINS = BIN_DENSE + 1;           // 14
+constexpr int BIN_DENSE_LOCAL = BIN_SORT0 + NUM_SORT;   // 13: bitmap path, column extent <= DENSE_LOCAL_COLS
+constexpr int BIN_DENSE = BIN_DENSE_LOCAL + 1;          // 14: bitmap path, wide rows
+constexpr int NUM_BINS = BIN_DENSE + 1;                 // 15
+constexpr int DENSE_LOCAL_BITS = 14;
+constexpr u32 DENSE_LOCAL_COLS = (1u << DENSE_LOCAL_BITS) - 128u;  // window starts chunk-aligned below the row minimum
 constexpr u32 SORT_MAX_PRODUCTS = 4u << (NUM_SORT - 1);  // 8192
 
 // Device-resident scalars of one multiply; mirrored into pinned host memory.
@@ -38,7 +41,7 @@ struct Scalars {
     u32 maxRowProducts;
     u32 binCount[NUM_BINS];   // rows per bin (written by k_analyze)
     u32 binCursor[NUM_BINS];  // scatter cursors (k_bin_scatter)
-    u32 denseCounter[2];      // dynamic row queues of the dense kernels (symbolic, numeric)
+    u32 denseCounter[4];      // dynamic row queues of the dense kernels (symbolic/numeric x local/wide)
     u32 tileCounter;          // dynamic tile ids of the scan
     u32 compareFlag;          // k_compare: 0 = equal
 };
@@ -49,12 +52,14 @@ struct CsrView {
     const void *v;
 };
 
-// bin of a row; -1 = no products at all
-__host__ __device__ __forceinline__ int classify_row(u32 ops, u32 aLen, u32 sortMax)
+// bin of a row; -1 = no products at all.  extent = maxCol - minCol + 1 of the row's products.
+// Rows whose column extent is at most four times their product count compress or are nearly dense: they take the bitmap path, which does not pay for the duplicates the way sorting does.
+__host__ __device__ __forceinline__ int classify_row(u32 ops, u32 aLen, u32 extent, u32 sortMax)
 {
     if (ops == 0) return -1;
     if (aLen == 1) return BIN_DIRECT;
-    if (ops > sortMax) return BIN_DENSE;
+    const bool banded = ops >= 128u && extent <= 4u * ops;
+    if (ops > sortMax || banded) return extent <= DENSE_LOCAL_COLS ? BIN_DENSE_LOCAL : BIN_DENSE;
     int c = 0;
     while ((4u << c) < ops) ++c;
     return BIN_SORT0 + c;
@@ -68,9 +73,9 @@ struct LaunchCtx {
 };
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
-                    u32 *rowOps, u32 *rowNnz, Scalars *sc, u32 sortMax);
-void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, u32 *perm,
-                        Scalars *sc, u32 sortMax);
+                    const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax);
+void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax);
 void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trailing total slot */,
                  u64 *tileState, Scalars *sc);
 size_t scan_tile_state_bytes(u32 n);
@@ -88,13 +93,15 @@ void launch_direct_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, cons
 
 // dense (bitmap) path; winBits = log2 of the column window held in shared memory
 int dense_window_bits(u64 colsB);
-void launch_dense_symbolic(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
-                           const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB, const u32 *rowOps,
-                           u32 *rowNnz);
+void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
+                           const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB,
+                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz);
+size_t dense_local_store_bytes(u32 count);
 template <typename T>
-void launch_dense_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
-                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
-                          u32 colsB, const u32 *rowOps, const u32 *cRp, u32 *cCi, T *cV);
+void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
+                          const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
+                          u32 colsB, const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, const u32 *cRp,
+                          u32 *cCi, T *cV);
 
 template <typename T>
 void launch_compare(const LaunchCtx &lc, u32 rows, const u32 *rpA, const u32 *ciA, const T *vA, const u32 *rpB,

@@ -20,7 +20,7 @@ namespace sb {
 
 constexpr int CHUNK_WORDS = 4;       // 128 columns per chunk = one 16-byte shared load
 constexpr int DENSE_MAX_WIN_BITS = 20;
-constexpr int DENSE_MIN_WIN_BITS = 12;  // 4096 columns = 32 chunks
+constexpr int DENSE_MIN_WIN_BITS = 14;  // 16384 columns
 
 int dense_window_bits(u64 colsB)
 {
@@ -72,14 +72,21 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *sWarp, u32 *tota
     return warpBase + incl - v;
 }
 
-// Shared-memory layout of one CTA (u32 words):
-//   bitmap[WWORDS] | chunkPrefix[NCHUNK] | touched[NCHUNK bytes] | sIncl[THREADS] | sBs[THREADS] | sAv[THREADS] (T)
-template <int THREADS, typename T, bool NUMERIC>
+// Shared-memory layout of one CTA:
+//   bitmap[WWORDS] u32 | chunkPrefix[NCHUNK] u32 | touched[NCHUNK] u8 | sIncl[THREADS] u32 | sBs[THREADS] u32 |
+//   sAv[THREADS] T | svals[SVALS] T
+// Windows are relative to the row: the first one starts at the row's smallest column (rounded down to
+// a chunk), so a banded row needs one small window wherever its band lies.
+// SVALS > 0: rows (windows) with at most SVALS distinct columns accumulate their values in shared
+// memory (atomicAdd on svals[rank]) and are written out coalesced; this is the path of high-compression
+// rows (FEM-like matrices), where a RED + column store per product would multiply the traffic to C.
+template <int THREADS, typename T, bool NUMERIC, int SVALS>
 __global__ void __launch_bounds__(THREADS)
 k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, const u32 *__restrict__ aRp,
              const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
-             const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 colsB, const int winBits,
-             const u32 *__restrict__ rowOps, u32 *cRp, u32 *__restrict__ cCi, T *cV)
+             const u32 *__restrict__ bCi, const T *__restrict__ bV, const int winBits,
+             const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax, u32 *bitmapStore, u32 *cRp,
+             u32 *__restrict__ cCi, T *cV)
 {
     extern __shared__ __align__(16) u32 dsm[];
     const u32 W = 1u << winBits;
@@ -91,28 +98,30 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
     u32 *sIncl = reinterpret_cast<u32 *>(touched + NCHUNK);
     u32 *sBs = sIncl + THREADS;
     T *sAv = reinterpret_cast<T *>(sBs + THREADS);
+    T *svals = sAv + THREADS;
+    constexpr u32 TAB = 2 * THREADS;   // owner table: one entry per 32 products of a batch
+    __shared__ unsigned short sTab[TAB];
     __shared__ u32 sWarp[32];
-    __shared__ u32 sRow, sMin, sMax;
+    __shared__ u32 sRow;
 
     const u32 tid = threadIdx.x;
     for (u32 i = tid; i < WWORDS; i += THREADS) bitmap[i] = 0;
     for (u32 i = tid; i < NCHUNK / 4; i += THREADS) reinterpret_cast<u32 *>(touched)[i] = 0;
-    const u32 numWin = (colsB + W - 1) >> winBits;
     const u32 CPT = (NCHUNK + THREADS - 1) / THREADS;  // consecutive chunks per thread
     const u32 chBeg = tid * CPT;
     const u32 chEnd = min(NCHUNK, chBeg + CPT);
 
-    // one batch = up to THREADS entries of the A row: B-row bounds trimmed to the window, inclusive
-    // scan of the lengths; products of the batch are then enumerated flat (p -> owner by binary
-    // search), so every thread gets the same number of products whatever the B-row lengths are.
-    auto load_batch = [&](u32 ab, u32 aEnd, u32 winLo, u32 winHi, u32 &nb) -> u32 {
+    // one batch = up to THREADS entries of the A row: B-row bounds (trimmed to the window when the row
+    // needs several), inclusive scan of the lengths; products of the batch are then enumerated flat
+    // (p -> owner by binary search), so every thread gets the same number of products.
+    auto load_batch = [&](u32 ab, u32 aEnd, bool trim, u32 winLo, u32 winHi, u32 &nb) -> u32 {
         nb = min((u32)THREADS, aEnd - ab);
         u32 bs = 0, len = 0;
         if (tid < nb) {
             const u32 k = __ldg(aCi + ab + tid);
             bs = __ldg(bRp + k);
             u32 be = __ldg(bRp + k + 1);
-            if (numWin > 1) {
+            if (trim) {
                 bs = lower_bound_dev(bCi, bs, be, winLo);
                 be = lower_bound_dev(bCi, bs, be, winHi);
             }
@@ -123,10 +132,22 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
         const u32 excl = block_exclusive_scan<THREADS>(len, sWarp, &total);
         sIncl[tid] = excl + len;
         sBs[tid] = bs - excl;  // q = sBs[owner] + p
+        // owner table: sTab[b] = entry that owns product 32*b (each entry fills the blocks it starts)
+        if (len && total <= 32u * TAB) {
+            const u32 bLast = (excl + len - 1) >> 5;
+            for (u32 b = (excl + 31) >> 5; b <= bLast; ++b) sTab[b] = (unsigned short)tid;
+        }
         __syncthreads();
         return total;
     };
-    auto owner_of = [&](u32 p, u32 nb) -> u32 {
+    // owner of product p: table entry, then a short forward walk (<= 32 steps); binary search only for
+    // batches with more than 32*TAB products
+    auto owner_of = [&](u32 p, u32 nb, u32 total) -> u32 {
+        if (total <= 32u * TAB) {
+            u32 o = sTab[p >> 5];
+            while (sIncl[o] <= p) ++o;
+            return o;
+        }
         u32 lo = 0, hi = nb;
         while (lo < hi) {
             const u32 mid = (lo + hi) >> 1;
@@ -137,49 +158,49 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
 
     while (true) {
         __syncthreads();
-        if (tid == 0) { sRow = atomicAdd(rowCounter, 1u); sMin = 0xffffffffu; sMax = 0u; }
+        if (tid == 0) sRow = atomicAdd(rowCounter, 1u);
         __syncthreads();
         const u32 ri = sRow;
         if (ri >= count) break;
         const u32 row = perm[ri];
         const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
         const bool oneBatch = (aEnd - aBeg) <= (u32)THREADS;
-
-        u32 winFirst = 0, winLast = 0;
-        if (numWin > 1) {  // column extent of the row -> windows to visit
-            u32 mn = 0xffffffffu, mx = 0u;
-            for (u32 a = aBeg + tid; a < aEnd; a += THREADS) {
-                const u32 k = __ldg(aCi + a);
-                const u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
-                if (be > bs) { mn = min(mn, __ldg(bCi + bs)); mx = max(mx, __ldg(bCi + be - 1)); }
-            }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-            }
-            if ((tid & 31) == 0) { atomicMin(&sMin, mn); atomicMax(&sMax, mx); }
-            __syncthreads();
-            winFirst = sMin >> winBits;
-            winLast = sMax >> winBits;
-        }
+        const u32 colMin = rowMin[row], colMax = rowMax[row];
+        const u32 base0 = colMin & ~(u32)(CHUNK_WORDS * 32 - 1);
+        const bool trim = (colMax - base0) >= W;  // more than one window
         const u32 rowStart = NUMERIC ? cRp[row] : 0u;
         u32 winBase = 0;
 
-        for (u32 win = winFirst; win <= winLast; ++win) {
-            const u32 winLo = win << winBits;
-            const u32 winHi = min(colsB, winLo + W);
+        for (u32 winLo = base0; winLo <= colMax; winLo += W) {
+            const u32 winHi = winLo + W;
             u32 nb = 0, total = 0;
-            // ------------------------------------------------ pass A: set column bits
-            for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
-                total = load_batch(ab, aEnd, winLo, winHi, nb);
-                for (u32 p = tid; p < total; p += THREADS) {
-                    const u32 o = owner_of(p, nb);
-                    const u32 c = __ldg(bCi + sBs[o] + p) - winLo;
-                    atomicOr(&bitmap[c >> 5], 1u << (c & 31));
-                    touched[c >> 7] = 1;
+            const u32 extWords = ((min(colMax, winHi - 1) - winLo) >> 5) + 1;
+            u32 *store = (bitmapStore && !trim) ? bitmapStore + (size_t)ri * WWORDS : nullptr;
+            if (NUMERIC && store) {
+                // ---------------------------------------------- the symbolic phase kept this row's bitmap
+                for (u32 i = tid; i < extWords; i += THREADS) {
+                    const u32 wv = store[i];
+                    bitmap[i] = wv;
+                    if (wv) touched[i >> 2] = 1;
                 }
+                if (oneBatch) total = load_batch(aBeg, aEnd, trim, winLo, winHi, nb);
                 __syncthreads();
+            } else {
+                // ---------------------------------------------- pass A: set column bits
+                for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
+                    total = load_batch(ab, aEnd, trim, winLo, winHi, nb);
+                    for (u32 p = tid; p < total; p += THREADS) {
+                        const u32 o = owner_of(p, nb, total);
+                        const u32 c = __ldg(bCi + sBs[o] + p) - winLo;
+                        atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+                        touched[c >> 7] = 1;
+                    }
+                    __syncthreads();
+                }
+                if (!NUMERIC && store) {  // keep the bitmap for the numeric phase
+                    for (u32 i = tid; i < extWords; i += THREADS) store[i] = bitmap[i];
+                    __syncthreads();
+                }
             }
             // ------------------------------------------------ chunk counts (touched chunks only)
             u32 tsum = 0;
@@ -198,17 +219,42 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
             const u32 texcl = block_exclusive_scan<THREADS>(tsum, sWarp, &winTotal);
 
             if (NUMERIC) {
-                for (u32 ch = chBeg; ch < chEnd; ++ch)
-                    if (touched[ch]) chunkPrefix[ch] += texcl + winBase;
-                // zero the value slots of this window; pass B adds into them with RED
-                for (u32 j = tid; j < winTotal; j += THREADS) cV[rowStart + winBase + j] = (T)0;
-                __threadfence_block();
+                const bool local = SVALS > 0 && winTotal <= (u32)SVALS;
+                const u32 outBase = rowStart + winBase;
+                for (u32 ch = chBeg; ch < chEnd; ++ch) {
+                    if (touched[ch]) {
+                        const u32 pfx = chunkPrefix[ch] + texcl;   // window-local rank of the chunk's first column
+                        chunkPrefix[ch] = pfx;
+                        if (local) {  // sorted column ids straight from the bitmap
+                            const uint4 v = *reinterpret_cast<const uint4 *>(&bitmap[ch * CHUNK_WORDS]);
+                            const u32 wv[4] = {v.x, v.y, v.z, v.w};
+                            u32 pos = outBase + pfx;
+                            const u32 colBase = winLo + ch * (CHUNK_WORDS * 32);
+#pragma unroll
+                            for (int wi = 0; wi < 4; ++wi) {
+                                u32 bits = wv[wi];
+                                while (bits) {
+                                    const u32 b = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    cCi[pos++] = colBase + wi * 32 + b;
+                                }
+                            }
+                        }
+                    }
+                }
+                // zero the accumulators of this window (shared or, for big windows, C itself)
+                if (local) {
+                    for (u32 j = tid; j < winTotal; j += THREADS) svals[j] = (T)0;
+                } else {
+                    for (u32 j = tid; j < winTotal; j += THREADS) cV[outBase + j] = (T)0;
+                    __threadfence_block();
+                }
                 __syncthreads();
-                // -------------------------------------------- pass B: rank -> column id + RED of the product
+                // -------------------------------------------- pass B: rank -> accumulate the product
                 for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
-                    if (!oneBatch) total = load_batch(ab, aEnd, winLo, winHi, nb);
+                    if (!oneBatch) total = load_batch(ab, aEnd, trim, winLo, winHi, nb);
                     for (u32 p = tid; p < total; p += THREADS) {
-                        const u32 o = owner_of(p, nb);
+                        const u32 o = owner_of(p, nb, total);
                         const u32 q = sBs[o] + p;
                         const u32 col = __ldg(bCi + q);
                         const T prod = sAv[o] * __ldg(bV + q);
@@ -220,12 +266,18 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                         const u32 below = (wi > 0 ? __popc(v.x) : 0) + (wi > 1 ? __popc(v.y) : 0) +
                                           (wi > 2 ? __popc(v.z) : 0);
                         const u32 word = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
-                        const u32 pos = rowStart + chunkPrefix[ch] + below + __popc(word & ((1u << (c & 31)) - 1u));
-                        cCi[pos] = col;  // every product of a column writes the same value
-                        atomicAdd(&cV[pos], prod);
+                        const u32 rank = chunkPrefix[ch] + below + __popc(word & ((1u << (c & 31)) - 1u));
+                        if (local) {
+                            atomicAdd(&svals[rank], prod);
+                        } else {
+                            cCi[outBase + rank] = col;  // every product of a column writes the same value
+                            atomicAdd(&cV[outBase + rank], prod);
+                        }
                     }
                     __syncthreads();
                 }
+                if (local)
+                    for (u32 j = tid; j < winTotal; j += THREADS) cV[outBase + j] = svals[j];
                 // -------------------------------------------- sparse clear
                 for (u32 ch = chBeg; ch < chEnd; ++ch) {
                     if (touched[ch]) {
@@ -241,61 +293,65 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
     }
 }
 
-template <int THREADS, typename T, bool NUMERIC>
-static void launch_dense_t(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
-                           const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, u32 colsB,
-                           const u32 *rowOps, u32 *cRp, u32 *cCi, T *cV)
+template <int THREADS, typename T, bool NUMERIC, int SVALS>
+static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u32 count, u32 *rowCounter,
+                           const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
+                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *cRp, u32 *cCi, T *cV)
 {
-    const int winBits = dense_window_bits(colsB);
-    const size_t smem = dense_smem_bytes(winBits, THREADS, sizeof(T));
-    auto kern = k_dense_rows<THREADS, T, NUMERIC>;
+    const size_t smem = dense_smem_bytes(winBits, THREADS, sizeof(T)) + (size_t)SVALS * sizeof(T);
+    auto kern = k_dense_rows<THREADS, T, NUMERIC, SVALS>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int perSm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, THREADS, smem);
     if (perSm < 1) perSm = 1;
     u32 grid = (u32)(lc.smCount * perSm);
     if (grid > count) grid = count;
-    kern<<<grid, THREADS, smem, lc.stream>>>(perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, colsB, winBits,
-                                             rowOps, cRp, cCi, cV);
+    kern<<<grid, THREADS, smem, lc.stream>>>(perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, winBits, rowMin,
+                                             rowMax, bitmapStore, cRp, cCi, cV);
     ++*lc.launches;
 }
 
-// CTA size: big windows leave room for one CTA per SM -> 1024 threads; small windows -> 256.
-static bool dense_big_cta(u64 colsB) { return dense_window_bits(colsB) >= 19; }
+// Two launch shapes:
+//   local : rows whose column extent fits DENSE_LOCAL_COLS -> 16 k-column window (2 KB bitmap), 256 threads,
+//           2048-entry shared value accumulator, ~8 CTAs per SM
+//   wide  : everything else -> window of up to 2^20 columns, 1024 threads (one or two CTAs per SM),
+//           4096-entry shared value accumulator
+size_t dense_local_store_bytes(u32 count) { return (size_t)count * ((size_t)1 << (DENSE_LOCAL_BITS - 5)) * sizeof(u32); }
 
-void launch_dense_symbolic(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
-                           const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB, const u32 *rowOps,
-                           u32 *rowNnz)
+void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
+                           const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB,
+                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz)
 {
     if (count == 0) return;
     const float *nv = nullptr;
-    if (dense_big_cta(colsB))
-        launch_dense_t<1024, float, false>(lc, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv, colsB, rowOps,
-                                           rowNnz, nullptr, nullptr);
+    if (local)
+        launch_dense_t<256, float, false, 0>(lc, DENSE_LOCAL_BITS, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv,
+                                             rowMin, rowMax, bitmapStore, rowNnz, nullptr, nullptr);
     else
-        launch_dense_t<256, float, false>(lc, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv, colsB, rowOps,
-                                          rowNnz, nullptr, nullptr);
+        launch_dense_t<1024, float, false, 0>(lc, dense_window_bits(colsB), perm, count, rowCounter, aRp, aCi, nv, bRp,
+                                              bCi, nv, rowMin, rowMax, nullptr, rowNnz, nullptr, nullptr);
 }
 
 template <typename T>
-void launch_dense_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, u32 *rowCounter, const u32 *aRp,
-                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
-                          u32 colsB, const u32 *rowOps, const u32 *cRp, u32 *cCi, T *cV)
+void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
+                          const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
+                          u32 colsB, const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, const u32 *cRp,
+                          u32 *cCi, T *cV)
 {
     if (count == 0) return;
     u32 *rp = const_cast<u32 *>(cRp);
-    if (dense_big_cta(colsB))
-        launch_dense_t<1024, T, true>(lc, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, colsB, rowOps, rp,
-                                      cCi, cV);
+    if (local)
+        launch_dense_t<256, T, true, 2048>(lc, DENSE_LOCAL_BITS, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV,
+                                           rowMin, rowMax, bitmapStore, rp, cCi, cV);
     else
-        launch_dense_t<256, T, true>(lc, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, colsB, rowOps, rp,
-                                     cCi, cV);
+        launch_dense_t<1024, T, true, 4096>(lc, dense_window_bits(colsB), perm, count, rowCounter, aRp, aCi, aV, bRp,
+                                            bCi, bV, rowMin, rowMax, nullptr, rp, cCi, cV);
 }
-template void launch_dense_numeric<double>(const LaunchCtx &, const u32 *, u32, u32 *, const u32 *, const u32 *,
+template void launch_dense_numeric<double>(const LaunchCtx &, bool, const u32 *, u32, u32 *, const u32 *, const u32 *,
                                            const double *, const u32 *, const u32 *, const double *, u32,
-                                           const u32 *, const u32 *, u32 *, double *);
-template void launch_dense_numeric<float>(const LaunchCtx &, const u32 *, u32, u32 *, const u32 *, const u32 *,
+                                           const u32 *, const u32 *, u32 *, const u32 *, u32 *, double *);
+template void launch_dense_numeric<float>(const LaunchCtx &, bool, const u32 *, u32, u32 *, const u32 *, const u32 *,
                                           const float *, const u32 *, const u32 *, const float *, u32,
-                                          const u32 *, const u32 *, u32 *, float *);
+                                          const u32 *, const u32 *, u32 *, const u32 *, u32 *, float *);
 
 }  // namespace sb

@@ -15,8 +15,10 @@ namespace sb {
 template <int LA>
 __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict__ aRp,
                                                  const u32 *__restrict__ aCi,
-                                                 const u32 *__restrict__ bRp, u32 *__restrict__ rowOps,
-                                                 u32 *__restrict__ rowNnz, Scalars *sc, u32 sortMax)
+                                                 const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
+                                                 u32 *__restrict__ rowOps, u32 *__restrict__ rowMin,
+                                                 u32 *__restrict__ rowMax, u32 *__restrict__ rowNnz, Scalars *sc,
+                                                 u32 sortMax)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -30,23 +32,37 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
     const u32 lane = threadIdx.x % LA;
     u64 ops64 = 0;
     u32 aLen = 0;
+    u32 cmin = 0xffffffffu, cmax = 0u;  // column extent of the row's products: B rows are sorted, so the
+                                        // first / last entry of each referenced B row bound it (the
+                                        // reference's rowColMinMax, common.cuh:395-400)
     if (row < rows) {
         const u32 beg = aRp[row], end = aRp[row + 1];
         aLen = end - beg;
         for (u32 p = beg + lane; p < end; p += LA) {
             const u32 k = __ldg(aCi + p);
-            ops64 += (u64)(__ldg(bRp + k + 1) - __ldg(bRp + k));
+            const u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
+            ops64 += (u64)(be - bs);
+            if (be > bs) {
+                cmin = min(cmin, __ldg(bCi + bs));
+                cmax = max(cmax, __ldg(bCi + be - 1));
+            }
         }
     }
 #pragma unroll
-    for (int d = LA / 2; d >= 1; d >>= 1) ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
+    for (int d = LA / 2; d >= 1; d >>= 1) {
+        ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, d));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+    }
     const u32 ops = ops64 > 0xffffffffull ? 0xffffffffu : (u32)ops64;
 
     u64 myProd = 0;
     u32 myMax = 0;
     if (row < rows && lane == 0) {
         rowOps[row] = ops;
-        const int bin = classify_row(ops, aLen, sortMax);
+        rowMin[row] = cmin;
+        rowMax[row] = cmax;
+        const int bin = classify_row(ops, aLen, ops ? cmax - cmin + 1u : 0u, sortMax);
         if (bin < 0)
             rowNnz[row] = 0;
         else {
@@ -75,20 +91,20 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 }
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
-                    u32 *rowOps, u32 *rowNnz, Scalars *sc, u32 sortMax)
+                    const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
     const int threads = 256;
     if (avg <= 3.0) {
         const u32 grid = (u32)(((u64)rows * 2 + threads - 1) / threads);
-        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, rowOps, rowNnz, sc, sortMax);
+        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax);
     } else if (avg <= 24.0) {
         const u32 grid = (u32)(((u64)rows * 8 + threads - 1) / threads);
-        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, rowOps, rowNnz, sc, sortMax);
+        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax);
     } else {
         const u32 grid = (u32)(((u64)rows * 32 + threads - 1) / threads);
-        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, rowOps, rowNnz, sc, sortMax);
+        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax);
     }
     ++*lc.launches;
 }
@@ -99,7 +115,9 @@ void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, con
 // + the <=6 D2D memcpys): one pass, one global atomic per (block, bin).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__restrict__ aRp,
-                                                     const u32 *__restrict__ rowOps, u32 *__restrict__ perm,
+                                                     const u32 *__restrict__ rowOps,
+                                                     const u32 *__restrict__ rowMin,
+                                                     const u32 *__restrict__ rowMax, u32 *__restrict__ perm,
                                                      Scalars *sc, u32 sortMax)
 {
     __shared__ u32 sCnt[NUM_BINS];
@@ -110,7 +128,8 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
     int bin = -1;
     u32 rank = 0;
     if (row < rows) {
-        bin = classify_row(rowOps[row], aRp[row + 1] - aRp[row], sortMax);
+        const u32 ops = rowOps[row];
+        bin = classify_row(ops, aRp[row + 1] - aRp[row], ops ? rowMax[row] - rowMin[row] + 1u : 0u, sortMax);
         if (bin >= 0) rank = atomicAdd(&sCnt[bin], 1u);
     }
     __syncthreads();
@@ -124,11 +143,11 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
     if (bin >= 0) perm[sBase[bin] + rank] = row;
 }
 
-void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, u32 *perm,
-                        Scalars *sc, u32 sortMax)
+void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax)
 {
     if (rows == 0) return;
-    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, perm, sc, sortMax);
+    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, rowMin, rowMax, perm, sc, sortMax);
     ++*lc.launches;
 }
 

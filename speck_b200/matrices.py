@@ -118,6 +118,29 @@ def banded_fem_like(n=62451, per_row=64, clusters=8, band=700, seed=41, dtype=np
     return from_coo(n, n, rows, cols, seed=seed + 100, dtype=dtype)
 
 
+def fem3d_like(nx=27, ny=27, nz=29, dof=3, seed=44, dtype=np.float64):
+    """cant-like FEM matrix: nx*ny*nz grid nodes, `dof` unknowns per node, 27-point stencil coupling
+    all dofs of neighbouring nodes (<= 81 entries per row).  A.A is the radius-2 stencil (<= 375
+    entries per row out of <= 6561 products: compression ~15, like SuiteSparse cant: n 62 451,
+    nnz 4.0 M, P 269.5 M, nnz(C) 17.4 M).  Default size: 63 423 rows."""
+    nodes = nx * ny * nz
+    idx = np.arange(nodes, dtype=np.int64)
+    x, y, z = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    rows, cols = [], []
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                ok = (x + dx >= 0) & (x + dx < nx) & (y + dy >= 0) & (y + dy < ny) & (z + dz >= 0) & (z + dz < nz)
+                src = idx[ok]
+                dst = src + dx + dy * nx + dz * nx * ny
+                for a in range(dof):
+                    for b in range(dof):
+                        rows.append(src * dof + a)
+                        cols.append(dst * dof + b)
+    n = nodes * dof
+    return from_coo(n, n, np.concatenate(rows), np.concatenate(cols), seed=seed + 100, dtype=dtype)
+
+
 def econ_like(n=206500, per_row=5.2, seed=42, dtype=np.float64):
     """mac_econ_like: diagonal + uniform random columns (compression ~1.1)."""
     rng = np.random.default_rng(seed)

@@ -8,6 +8,11 @@ from speck_b200 import matrices as M
 from speck_b200.matrices import HostCSR
 from helpers import check_case, gpu_multiply, oracle_multiply, assert_csr_equal
 
+
+def ndense(st):
+    """rows that took the bitmap path (either launch shape)"""
+    return st["class_rows"]["dense"] + st["class_rows"]["dense_local"]
+
 pytestmark = pytest.mark.gpu
 
 
@@ -35,7 +40,7 @@ def test_rmat(ctx, sort_max, scale, ef):
     A = M.rmat(scale, ef, seed=scale)
     got, st = check_case(ctx, A, what=f"rmat{scale} sort_max={sort_max}")
     if sort_max <= 1024 and scale >= 13:
-        assert st["class_rows"]["dense"] > 0
+        assert ndense(st) > 0
     if sort_max == 8192 and scale >= 15:
         assert st["class_rows"]["sort2048"] > 0 and st["class_rows"]["sort4096"] > 0
 
@@ -80,9 +85,9 @@ def test_class_boundaries(ctx):
         b = 4 << c
         targets += [b - 1, b, b + 1]
     targets += [1, 2, 3, 8255, 8256]
-    A, B = _rows_with_products(targets, cols=16384)
+    A, B = _rows_with_products(targets, cols=1 << 18)
     got, st = check_case(ctx, A, B, what="class boundaries")
-    assert st["class_rows"]["dense"] >= 3
+    assert ndense(st) >= 3
     for name in ("sort1024", "sort2048", "sort4096", "sort8192"):
         assert st["class_rows"][name] >= 3, name
 
@@ -147,7 +152,8 @@ def test_empty_products_conventions(ctx):
 def test_banded_high_compression(ctx, sort_max):
     A = M.banded_fem_like(n=3000, per_row=64, clusters=8, band=300, seed=41)
     got, st = check_case(ctx, A, what=f"banded sort_max={sort_max}")
-    assert (st["class_rows"]["dense"] > 0) == (sort_max < 4096)
+    # column extent (<= 2*300+8) is far below the 4096 products of a row: bitmap path whatever sort_max is
+    assert st["class_rows"]["dense_local"] > 2500
 
 
 def test_wide_matrix_multiwindow_and_wide_keys(ctx, sort_max):
@@ -166,6 +172,22 @@ def test_wide_matrix_multiwindow_and_wide_keys(ctx, sort_max):
     got, st = check_case(ctx, A, B, what=f"wide sort_max={sort_max}")
     if sort_max <= 1024:
         assert st["class_rows"]["dense"] >= 4
+
+
+def test_fem_like_high_compression(ctx):
+    """27-point stencil x 3 dofs: ~6500 products fold into ~375 columns per row -> bitmap path with
+    the shared-memory value accumulator; also exercises rows wider than one local window."""
+    A = M.fem3d_like(9, 8, 7)
+    got, st = check_case(ctx, A, what="fem3d")
+    assert st["class_rows"]["dense_local"] > 0
+    assert st["products"] > 8 * st["nnz_c"]
+
+
+def test_dense_rows_exceeding_shared_accumulator(ctx):
+    """banded rows with more distinct columns than the 2048-entry shared accumulator -> RED path"""
+    A = M.banded_fem_like(n=6000, per_row=96, clusters=12, band=1500, seed=7)
+    got, st = check_case(ctx, A, what="wide band")
+    assert ndense(st) > 0
 
 
 def test_fp32(ctx):
@@ -221,6 +243,6 @@ def test_sort_max_option_routes_more_rows_to_dense(ctx):
     ctx.set_option("sort_max", 64)
     try:
         got, st = check_case(ctx, A, what="sort_max=64")
-        assert st["class_rows"]["sort128"] == 0 and st["class_rows"]["dense"] > 0
+        assert st["class_rows"]["sort128"] == 0 and ndense(st) > 0
     finally:
         ctx.set_option("sort_max", 8192)
