@@ -19,10 +19,10 @@ void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, const u32 *perm, u
         case 5: SB_SYM(32, 4); break;
         case 6: SB_SYM(32, 8); break;
         case 7: SB_SYM(32, 16); break;
-        case 8: SB_SYM(32, 32); break;
-        case 9: launch_sort_rows_cta<2, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
-        case 10: launch_sort_rows_cta<4, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
-        case 11: launch_sort_rows_cta<8, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
+        case 8: launch_sort_rows_cta<2, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
+        case 9: launch_sort_rows_cta<4, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
+        case 10: launch_sort_rows_cta<8, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
+        case 11: launch_sort_rows_cta<16, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
         default: break;
     }
 #undef SB_SYM

@@ -1,35 +1,37 @@
 // speck_b200/csrc/sort_cta.cuh -- multi-warp sort classes: one CTA of WARPS warps per row of C,
-// N = WARPS * 1024 products.  Same three steps as sort_rows.cuh (gather / bitonic sort / fold +
-// emit); each warp keeps 1024 keys in registers (32 per lane), merge stages whose partner distance
-// reaches 1024 exchange keys through shared memory, everything below runs on shuffles/registers.
+// N = WARPS * 32 * E products (E = 16 keys per lane).  Same three steps as sort_rows.cuh (gather / bitonic sort / fold +
+// emit); each warp keeps 32*E keys in registers, merge stages whose partner distance
+// reaches 32*E exchange keys through shared memory, everything below runs on shuffles/registers.
 // Products are enumerated flat over the CTA (block scan of B-row lengths + binary search).
 #pragma once
 #include "sort_rows.cuh"
 
 namespace sb {
 
-template <int WARPS, typename KeyT, typename T, bool NUMERIC>
+template <int WARPS, int E, typename KeyT, typename T, bool NUMERIC>
 struct CtaSortLayout {
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int N = WARPS * 1024;
+    static constexpr int WN = 32 * E;          // keys per warp
+    static constexpr int N = WARPS * WN;
     static constexpr int NPAD = N + N / 32;
     static constexpr size_t KEY_BYTES = ((size_t)NPAD * sizeof(KeyT) + 15) / 16 * 16;
     static constexpr size_t VAL_BYTES = NUMERIC ? (size_t)N * sizeof(T) : 0;
     static constexpr size_t BATCH_BYTES = (size_t)THREADS * (8 + (NUMERIC ? sizeof(T) : 0));
-    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + BATCH_BYTES;
+    static constexpr size_t TAB_BYTES = (size_t)(N / 32) * sizeof(unsigned short);
+    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + BATCH_BYTES + TAB_BYTES;
 };
 
-template <int WARPS, typename KeyT, typename T, bool NUMERIC>
+template <int WARPS, int E, typename KeyT, typename T, bool NUMERIC>
 __global__ void __launch_bounds__(WARPS * 32)
 k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
                 const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
                 const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
                 u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV)
 {
-    using L = CtaSortLayout<WARPS, KeyT, T, NUMERIC>;
+    using L = CtaSortLayout<WARPS, E, KeyT, T, NUMERIC>;
     constexpr int THREADS = L::THREADS;
     constexpr int N = L::N;
-    constexpr int E = 32;
+    constexpr int WN = L::WN;
     constexpr int IDXBITS = Log2<N>::value;
     constexpr KeyT SENT = ~(KeyT)0;
     constexpr u32 FULL = 0xffffffffu;
@@ -39,6 +41,7 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
     u32 *sIncl = reinterpret_cast<u32 *>(smemRaw + L::KEY_BYTES + L::VAL_BYTES);
     u32 *sBs = sIncl + THREADS;
     T *sAv = reinterpret_cast<T *>(sBs + THREADS);
+    unsigned short *sTab = reinterpret_cast<unsigned short *>(smemRaw + L::KEY_BYTES + L::VAL_BYTES + L::BATCH_BYTES);
     __shared__ u32 sWarp[32];
     __shared__ KeyT sLast[WARPS];
 
@@ -78,13 +81,16 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
         incl += warpBase;
         sIncl[tid] = incl;
         sBs[tid] = bs - (incl - len);  // q = sBs[owner] + p
+        if (len) {  // owner table: sTab[b] = entry owning product 32*b (total <= N, so N/32 entries suffice)
+            const u32 excl = incl - len;
+            const u32 bLast = (incl - 1) >> 5;
+            for (u32 b = (excl + 31) >> 5; b <= bLast; ++b) sTab[b] = (unsigned short)tid;
+        }
         __syncthreads();
+#pragma unroll 4
         for (u32 p = tid; p < total; p += THREADS) {
-            u32 lo = 0, hi = nb;
-            while (lo < hi) {
-                const u32 mid = (lo + hi) >> 1;
-                if (sIncl[mid] <= p) lo = mid + 1; else hi = mid;
-            }
+            u32 lo = sTab[p >> 5];
+            while (sIncl[lo] <= p) ++lo;
             const u32 q = sBs[lo] + p;
             const u32 col = __ldg(bCi + q);
             const u32 gp = base + p;
@@ -100,22 +106,25 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
     }
 
     // ---------------------------------------------------------------- sort
-    // logical index of (warp w, lane l, register r) = w*1024 + l*32 + r
+    // logical index of (warp w, lane l, register r) = w*WN + l*E + r
     KeyT reg[E];
 #pragma unroll
     for (int r = 0; r < E; ++r) {
-        const u32 idx = w * 1024 + r * 32 + l;  // conflict-free read; any bijection is fine before sorting
+        const u32 idx = w * WN + r * 32 + l;  // conflict-free read; any bijection is fine before sorting
         reg[r] = idx < ops ? keys[idx] : SENT;
     }
     __syncthreads();
-    bitonic_sort_regs<32, E, KeyT>(reg, l, FULL);  // every warp: its 1024 keys ascending
-    const u32 myBase = w * 1024 + l * 32;
-#pragma unroll
-    for (int k = 2048; k <= N; k <<= 1) {
-        // mirrored stage across warps, then cross-warp half cleaners (j >= 1024) through shared memory
-#pragma unroll
-        for (int j = k; j >= 1024; j >>= 1) {
-            if (j == k >> 1) continue;  // stages are: mirror (encoded as j == k), then j = k/4, k/8, ...
+    bitonic_sort_regs<32, E, KeyT>(reg, l, FULL);  // every warp: its WN keys ascending
+    const u32 myBase = w * WN + l * E;
+    // merge levels across warps.  The loops are NOT unrolled: one copy of the exchange code and of the
+    // in-warp half cleaners keeps the kernel inside the instruction cache (a fully unrolled 1024-key
+    // network stalls ~60 % of its issue slots on instruction fetch, profiles/r1_icache.md).
+#pragma unroll 1
+    for (int k = 2 * WN; k <= N; k <<= 1) {
+        // mirrored stage (encoded as j == k), then cross-warp half cleaners j = k/4 ... WN
+#pragma unroll 1
+        for (int j = k; j >= WN; j >>= 1) {
+            if (j == k >> 1) continue;
 #pragma unroll
             for (int r = 0; r < E; ++r) {
                 const u32 idx = myBase + r;
@@ -123,7 +132,7 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
             }
             __syncthreads();
             const u32 x = (j == k) ? (u32)(k - 1) : (u32)j;
-            const bool lower = (j == k) ? ((w & (k / 2048)) == 0) : ((w & (j / 1024)) == 0);
+            const bool lower = (j == k) ? ((w & (k / (2 * WN))) == 0) : ((w & (j / WN)) == 0);
 #pragma unroll
             for (int r = 0; r < E; ++r) {
                 const u32 pidx = (myBase + r) ^ x;
@@ -132,7 +141,7 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
             }
             __syncthreads();
         }
-        bitonic_half_cleaners<32, E, KeyT>(reg, l, FULL, 512);
+        bitonic_half_cleaners<32, E, KeyT>(reg, l, FULL, WN / 2);
     }
 
     if (!NUMERIC) {
@@ -169,8 +178,8 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
         }
         __syncthreads();
         constexpr KeyT IDXMASK = ((KeyT)1 << IDXBITS) - 1;
-        const u32 segBeg = w * 1024;
-        const u32 segEnd = min(ops, segBeg + 1024);
+        const u32 segBeg = w * WN;
+        const u32 segEnd = min(ops, segBeg + WN);
         // pass 1: heads in this warp's segment
         u32 heads = 0;
         for (u32 i0 = segBeg; i0 < segEnd; i0 += 32) {
@@ -217,13 +226,13 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
     }
 }
 
-template <int WARPS, typename KeyT, typename T, bool NUMERIC>
+template <int WARPS, int E, typename KeyT, typename T, bool NUMERIC>
 void launch_sort_rows_cta(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                           const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, u32 *cRp,
                           u32 *cCi, T *cV)
 {
-    using L = CtaSortLayout<WARPS, KeyT, T, NUMERIC>;
-    auto kern = k_sort_rows_cta<WARPS, KeyT, T, NUMERIC>;
+    using L = CtaSortLayout<WARPS, E, KeyT, T, NUMERIC>;
+    auto kern = k_sort_rows_cta<WARPS, E, KeyT, T, NUMERIC>;
     if (L::SMEM > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
     kern<<<count, L::THREADS, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV);

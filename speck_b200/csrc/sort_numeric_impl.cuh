@@ -22,9 +22,9 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
 #define SB_NUM_CTA(W)                                                                                        \
     do {                                                                                                     \
         if (wideKeys)                                                                                        \
-            launch_sort_rows_cta<W, u64, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+            launch_sort_rows_cta<W, 16, u64, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
         else                                                                                                 \
-            launch_sort_rows_cta<W, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+            launch_sort_rows_cta<W, 16, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
     } while (0)
     switch (sortClass) {
         case 0: SB_NUM(4, 1); break;
@@ -35,10 +35,10 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
         case 5: SB_NUM(32, 4); break;
         case 6: SB_NUM(32, 8); break;
         case 7: SB_NUM(32, 16); break;
-        case 8: SB_NUM(32, 32); break;
-        case 9: SB_NUM_CTA(2); break;
-        case 10: SB_NUM_CTA(4); break;
-        case 11: SB_NUM_CTA(8); break;
+        case 8: SB_NUM_CTA(2); break;
+        case 9: SB_NUM_CTA(4); break;
+        case 10: SB_NUM_CTA(8); break;
+        case 11: SB_NUM_CTA(16); break;
         default: break;
     }
 #undef SB_NUM
