@@ -189,11 +189,25 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                 // ---------------------------------------------- pass A: set column bits
                 for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
                     total = load_batch(ab, aEnd, trim, winLo, winHi, nb);
-                    for (u32 p = tid; p < total; p += THREADS) {
-                        const u32 o = owner_of(p, nb, total);
-                        const u32 c = __ldg(bCi + sBs[o] + p) - winLo;
-                        atomicOr(&bitmap[c >> 5], 1u << (c & 31));
-                        touched[c >> 7] = 1;
+                    // four products per thread and iteration: the four column loads are in flight together
+                    for (u32 p0 = tid; p0 < total; p0 += 4 * THREADS) {
+                        u32 q[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const u32 p = p0 + u * THREADS;
+                            q[u] = p < total ? sBs[owner_of(p, nb, total)] + p : 0xffffffffu;
+                        }
+                        u32 cc[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cc[u] = q[u] != 0xffffffffu ? __ldg(bCi + q[u]) : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (q[u] != 0xffffffffu) {
+                                const u32 c = cc[u] - winLo;
+                                atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+                                touched[c >> 7] = 1;
+                            }
+                        }
                     }
                     __syncthreads();
                 }
@@ -253,11 +267,30 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                 // -------------------------------------------- pass B: rank -> accumulate the product
                 for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
                     if (!oneBatch) total = load_batch(ab, aEnd, trim, winLo, winHi, nb);
-                    for (u32 p = tid; p < total; p += THREADS) {
-                        const u32 o = owner_of(p, nb, total);
-                        const u32 q = sBs[o] + p;
-                        const u32 col = __ldg(bCi + q);
-                        const T prod = sAv[o] * __ldg(bV + q);
+                    for (u32 p0 = tid; p0 < total; p0 += 4 * THREADS) {
+                      u32 qq[4], colv[4];
+                      T avv[4], bvv[4];
+#pragma unroll
+                      for (int u = 0; u < 4; ++u) {
+                          const u32 p = p0 + u * THREADS;
+                          qq[u] = 0xffffffffu;
+                          avv[u] = (T)0;
+                          if (p < total) {
+                              const u32 o = owner_of(p, nb, total);
+                              qq[u] = sBs[o] + p;
+                              avv[u] = sAv[o];
+                          }
+                      }
+#pragma unroll
+                      for (int u = 0; u < 4; ++u) {
+                          colv[u] = qq[u] != 0xffffffffu ? __ldg(bCi + qq[u]) : 0u;
+                          bvv[u] = qq[u] != 0xffffffffu ? __ldg(bV + qq[u]) : (T)0;
+                      }
+#pragma unroll
+                      for (int u = 0; u < 4; ++u) {
+                        if (qq[u] == 0xffffffffu) continue;
+                        const u32 col = colv[u];
+                        const T prod = avv[u] * bvv[u];
                         const u32 c = col - winLo;
                         const u32 w = c >> 5;
                         const u32 ch = w >> 2;
@@ -273,6 +306,7 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                             cCi[outBase + rank] = col;  // every product of a column writes the same value
                             atomicAdd(&cV[outBase + rank], prod);
                         }
+                      }
                     }
                     __syncthreads();
                 }

@@ -87,18 +87,37 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
             for (u32 b = (excl + 31) >> 5; b <= bLast; ++b) sTab[b] = (unsigned short)tid;
         }
         __syncthreads();
-#pragma unroll 4
-        for (u32 p = tid; p < total; p += THREADS) {
-            u32 lo = sTab[p >> 5];
-            while (sIncl[lo] <= p) ++lo;
-            const u32 q = sBs[lo] + p;
-            const u32 col = __ldg(bCi + q);
-            const u32 gp = base + p;
-            if (NUMERIC) {
-                keys[gp] = ((KeyT)col << IDXBITS) | (KeyT)gp;
-                vals[gp] = sAv[lo] * __ldg(bV + q);
-            } else {
-                keys[gp] = (KeyT)col;
+        // four products per thread and iteration: owners first, then all loads, then the stores
+        for (u32 p0 = tid; p0 < total; p0 += 4 * THREADS) {
+            u32 q[4], col[4];
+            T av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const u32 p = p0 + u * THREADS;
+                q[u] = 0xffffffffu;
+                av[u] = (T)0;
+                if (p < total) {
+                    u32 lo = sTab[p >> 5];
+                    while (sIncl[lo] <= p) ++lo;
+                    q[u] = sBs[lo] + p;
+                    if (NUMERIC) av[u] = sAv[lo];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                col[u] = q[u] != 0xffffffffu ? __ldg(bCi + q[u]) : 0u;
+                bv[u] = (NUMERIC && q[u] != 0xffffffffu) ? __ldg(bV + q[u]) : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (q[u] == 0xffffffffu) continue;
+                const u32 gp = base + p0 + u * THREADS;
+                if (NUMERIC) {
+                    keys[gp] = ((KeyT)col[u] << IDXBITS) | (KeyT)gp;
+                    vals[gp] = av[u] * bv[u];
+                } else {
+                    keys[gp] = (KeyT)col[u];
+                }
             }
         }
         base += total;
