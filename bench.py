@@ -146,6 +146,31 @@ def time_oracle(As: HostCSR, B: HostCSR, reps=1):
     return P, best
 
 
+def time_reference_gpu(args):
+    """The reference's own CUDA build (sm_100, oracle/_ref) on the same GPU and workload, in a
+    subprocess (a crash of the reference must not take the bench down).  Reported next to our line;
+    it is NOT the `--impl reference` arm (that one is the CPU port, per the bench contract)."""
+    out = {}
+    for variant in ("stock", "tuned"):
+        so = os.path.join(ROOT, "oracle", "_ref", f"libspeck_ref_{variant}.so")
+        if not os.path.exists(so):
+            out[variant] = {"unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
+            continue
+        try:
+            r = subprocess.run([sys.executable, "-m", "oracle.ref_run", "--workload", args.workload, "--seed", str(args.seed),
+                                "--variant", variant, "--warmup", "3", "--iters", "5"],
+                               capture_output=True, text=True, timeout=600, cwd=ROOT)
+            js = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            d = json.loads(js[-1]) if js else {"error": r.stderr[-200:]}
+            out[variant] = {k: d[k] for k in ("mean_ms", "min_ms", "gflops_mean", "gflops_best", "nnz_c") if k in d} or d
+        except Exception as e:  # noqa: BLE001
+            out[variant] = {"error": repr(e)}
+    best = max((v.get("gflops_mean", 0.0) for v in out.values()), default=0.0)
+    out["best_gflops_mean"] = best
+    out["note"] = "reference spECK compiled for sm_100 (stock 49152/49152 and tuned dynamic smem 232448), timings.complete, C reused"
+    return out
+
+
 def run_reference_arm(args, rank, world):
     """CPU oracle (port; the reference has no CPU SpGEMM) on all host cores, rank 0 only."""
     if rank != 0:
@@ -188,6 +213,8 @@ def main():
     ap.add_argument("--cpu-stride", type=int, default=4, help="row stride of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true",
+                    help="skip timing the reference spECK CUDA build (oracle/_ref) on the same GPU")
     ap.add_argument("--sort-max", type=int, default=0)
     args = ap.parse_args()
 
@@ -363,6 +390,8 @@ def main():
             line["cpu_baseline"] = {"value": 2.0 * Pc / tc / 1e9, "unit": "GFLOPS", "cores": oracle.num_threads(),
                                     "kind": "port",
                                     "sample": f"every {args.cpu_stride}th row of A ({As.rows} rows, P={Pc}) x full B, {tc:.2f} s"}
+        if not args.no_ref_gpu and world == 1:
+            line["ref_speck_gpu"] = time_reference_gpu(args)
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         try:
             line["roofline"]["traffic"] = json.load(open(prof)).get(args.workload)

@@ -63,7 +63,7 @@ typedef struct speck_timings {
         complete;
 } speck_timings;
 
-#define SPECK_NUM_CLASSES 16
+#define SPECK_NUM_CLASSES 32
 
 /* What the last multiply did (for bench.py's roofline arithmetic and the tests). */
 typedef struct speck_stats {

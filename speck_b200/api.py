@@ -20,9 +20,9 @@ from .matrices import HostCSR
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libspeck_b200.so")
 
-NUM_CLASSES = 16
-BIN_NAMES = ["direct", "sort4", "sort8", "sort16", "sort32", "sort64", "sort128", "sort256",
-             "sort512", "sort1024", "sort2048", "sort4096", "sort8192", "dense_local", "dense"]
+NUM_CLASSES = 32
+BIN_NAMES = (["direct"] + [f"sort{4 << c}" for c in range(8)] + [f"sort{512 * w}" for w in range(2, 17)]
+             + ["dense_local", "dense"])
 
 
 class SpeckError(RuntimeError):

@@ -134,7 +134,11 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // CTA-level sort classes (> 1024 products) are used only while (col << log2 N) fits a u32 key;
     // wider matrices send those rows to the bitmap path instead of sorting u64 keys.
     u32 sortMax = c->sortMax;
-    while (sortMax > 1024 && ((u64)colsB * sortMax) > (1ull << 32)) sortMax >>= 1;
+    if (sortMax > 1024) {  // largest power-of-two network whose keys fit 32 bits: cols * N <= 2^32
+        u32 fit = 8192;
+        while (fit > 1024 && ((u64)colsB * fit) > (1ull << 32)) fit >>= 1;
+        if (sortMax > fit) sortMax = fit;
+    }
 
     // ---- init: workspace, C.row_offsets (reuse rule of Multiply.cu:155-165)
     cudaEventRecord(c->evStage[0], c->main);
@@ -244,7 +248,12 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
-        const bool wide = ((u64)colsB << (2 + sc)) > (1ull << 32);
+        u32 npow2 = 4u << sc;  // lane-group classes
+        if (sc >= NUM_WARP_SORT) {
+            npow2 = 1024;
+            while (npow2 < 512u * (u32)(sc - NUM_WARP_SORT + 2)) npow2 <<= 1;
+        }
+        const bool wide = ((u64)colsB * npow2) > (1ull << 32);
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
         launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
                                cRp, cCi, cV);
@@ -561,8 +570,8 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
 {
     if (!c || !key) return fail(SPECK_ERR_INVALID, "null argument");
     if (!strcmp(key, "sort_max")) {
-        if (value < 4 || value > (long long)SORT_MAX_PRODUCTS || (value & (value - 1)))
-            return fail(SPECK_ERR_INVALID, "sort_max must be a power of two in [4, %u]", SORT_MAX_PRODUCTS);
+        if (value < 4 || value > (long long)SORT_MAX_PRODUCTS || ((value & (value - 1)) && value % 512))
+            return fail(SPECK_ERR_INVALID, "sort_max must be a power of two or a multiple of 512 in [4, %u]", SORT_MAX_PRODUCTS);
         c->sortMax = (u32)value;
         return SPECK_OK;
     }

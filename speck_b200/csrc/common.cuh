@@ -6,8 +6,8 @@
 // Row classes ("bins"):
 //   BIN_DIRECT        A row has exactly one entry: C row = scaled copy of one B row
 //                     (reference: directSpGEMM*, spECK_HashSpGEMM.cuh:543-589)
-//   BIN_SORT0 + c     products <= 4<<c (c = 0..11): register bitonic sort of the row's
-//                     products by a lane group (c <= 8) or a CTA of 2/4/8 warps (c = 9..11),
+//   BIN_SORT0 + c     products <= 4<<c (c = 0..7): register bitonic sort of the row's products by a
+//                     lane group; c = 8..22: by a CTA of 2..16 warps (512 keys per warp),
 //                     duplicates folded after the sort
 //                     (replaces the smem hash + O(n^2) rank sort, :591-866)
 //   BIN_DENSE         more products: CTA per row, sparse-cleared column bitmap in
@@ -23,16 +23,17 @@ typedef uint64_t u64;
 
 namespace sb {
 
-constexpr int NUM_SORT = 12;                // sort classes: 4, 8, ..., 1024 (one lane group) and 2048, 4096, 8192 (one CTA)
-constexpr int NUM_WARP_SORT = 9;
+constexpr int NUM_WARP_SORT = 8;            // lane-group classes: 4, 8, ..., 512 products
+constexpr int NUM_CTA_SORT = 15;            // CTA classes: 2..16 warps x 512 keys = 1024, 1536, ..., 8192 products
+constexpr int NUM_SORT = NUM_WARP_SORT + NUM_CTA_SORT;
 constexpr int BIN_DIRECT = 0;
 constexpr int BIN_SORT0 = 1;
-constexpr int BIN_DENSE_LOCAL = BIN_SORT0 + NUM_SORT;   // 13: bitmap path, column extent <= DENSE_LOCAL_COLS
-constexpr int BIN_DENSE = BIN_DENSE_LOCAL + 1;          // 14: bitmap path, wide rows
-constexpr int NUM_BINS = BIN_DENSE + 1;                 // 15
+constexpr int BIN_DENSE_LOCAL = BIN_SORT0 + NUM_SORT;   // 24: bitmap path, column extent <= DENSE_LOCAL_COLS
+constexpr int BIN_DENSE = BIN_DENSE_LOCAL + 1;          // 25: bitmap path, wide rows
+constexpr int NUM_BINS = BIN_DENSE + 1;                 // 26
 constexpr int DENSE_LOCAL_BITS = 14;
 constexpr u32 DENSE_LOCAL_COLS = (1u << DENSE_LOCAL_BITS) - 128u;  // window starts chunk-aligned below the row minimum
-constexpr u32 SORT_MAX_PRODUCTS = 4u << (NUM_SORT - 1);  // 8192
+constexpr u32 SORT_MAX_PRODUCTS = 8192;
 
 // Device-resident scalars of one multiply; mirrored into pinned host memory.
 struct Scalars {
@@ -60,6 +61,7 @@ __host__ __device__ __forceinline__ int classify_row(u32 ops, u32 aLen, u32 exte
     if (aLen == 1) return BIN_DIRECT;
     const bool banded = ops >= 128u && extent <= 4u * ops;
     if (ops > sortMax || banded) return extent <= DENSE_LOCAL_COLS ? BIN_DENSE_LOCAL : BIN_DENSE;
+    if (ops > 512u) return BIN_SORT0 + NUM_WARP_SORT + (int)((ops + 511u) / 512u) - 2;  // 2..16 warps
     int c = 0;
     while ((4u << c) < ops) ++c;
     return BIN_SORT0 + c;

@@ -19,11 +19,16 @@ void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, const u32 *perm, u
         case 5: SB_SYM(32, 4); break;
         case 6: SB_SYM(32, 8); break;
         case 7: SB_SYM(32, 16); break;
-        case 8: launch_sort_rows_cta<2, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
-        case 9: launch_sort_rows_cta<4, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
-        case 10: launch_sort_rows_cta<8, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
-        case 11: launch_sort_rows_cta<16, 16, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr); break;
-        default: break;
+        default: {
+            const int warps = cta_class_warps(sortClass - NUM_WARP_SORT);
+#define SB_SYM_CTA(WMAX) launch_sort_rows_cta<WMAX, 16, u32, float, false>(lc, warps, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr)
+            if (warps <= 2) SB_SYM_CTA(2);
+            else if (warps <= 4) SB_SYM_CTA(4);
+            else if (warps <= 8) SB_SYM_CTA(8);
+            else SB_SYM_CTA(16);
+#undef SB_SYM_CTA
+            break;
+        }
     }
 #undef SB_SYM
 }

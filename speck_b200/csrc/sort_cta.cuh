@@ -8,42 +8,45 @@
 
 namespace sb {
 
-template <int WARPS, int E, typename KeyT, typename T, bool NUMERIC>
+// Shared-memory layout for a CTA of `warps` warps (runtime, WMAX/2 < warps <= WMAX):
+//   keys[n + n/32] | vals[n] (numeric) | sIncl[threads] | sBs[threads] | sAv[threads] (numeric) | sTab[n/32]
+template <int E, typename KeyT, typename T, bool NUMERIC>
 struct CtaSortLayout {
-    static constexpr int THREADS = WARPS * 32;
     static constexpr int WN = 32 * E;          // keys per warp
-    static constexpr int N = WARPS * WN;
-    static constexpr int NPAD = N + N / 32;
-    static constexpr size_t KEY_BYTES = ((size_t)NPAD * sizeof(KeyT) + 15) / 16 * 16;
-    static constexpr size_t VAL_BYTES = NUMERIC ? (size_t)N * sizeof(T) : 0;
-    static constexpr size_t BATCH_BYTES = (size_t)THREADS * (8 + (NUMERIC ? sizeof(T) : 0));
-    static constexpr size_t TAB_BYTES = (size_t)(N / 32) * sizeof(unsigned short);
-    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + BATCH_BYTES + TAB_BYTES;
+    __host__ __device__ static size_t key_bytes(int warps) { return ((size_t)(warps * WN + warps * WN / 32) * sizeof(KeyT) + 15) / 16 * 16; }
+    __host__ __device__ static size_t val_bytes(int warps) { return NUMERIC ? (size_t)warps * WN * sizeof(T) : 0; }
+    __host__ __device__ static size_t batch_bytes(int warps) { return (size_t)warps * 32 * (8 + (NUMERIC ? sizeof(T) : 0)); }
+    __host__ __device__ static size_t tab_bytes(int warps) { return (size_t)(warps * WN / 32) * sizeof(unsigned short); }
+    __host__ __device__ static size_t smem(int warps) { return key_bytes(warps) + val_bytes(warps) + batch_bytes(warps) + tab_bytes(warps); }
 };
 
-template <int WARPS, int E, typename KeyT, typename T, bool NUMERIC>
-__global__ void __launch_bounds__(WARPS * 32)
+// WMAX = power of two >= the CTA's warp count: fixes the index bits of the keys and the depth of the
+// merge network; warps beyond blockDim.x/32 are virtual (all +inf) and every exchange with them is a
+// no-op, so a row with 1300 products is sorted by 3 warps (1536 slots) instead of 4 (2048).
+template <int WMAX, int E, typename KeyT, typename T, bool NUMERIC>
+__global__ void __launch_bounds__(WMAX * 32)
 k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
                 const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
                 const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
                 u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV)
 {
-    using L = CtaSortLayout<WARPS, E, KeyT, T, NUMERIC>;
-    constexpr int THREADS = L::THREADS;
-    constexpr int N = L::N;
+    using L = CtaSortLayout<E, KeyT, T, NUMERIC>;
+    const int WARPS = blockDim.x >> 5;
+    const u32 THREADS = blockDim.x;
     constexpr int WN = L::WN;
-    constexpr int IDXBITS = Log2<N>::value;
+    constexpr int NPOW2 = WMAX * WN;
+    constexpr int IDXBITS = Log2<NPOW2>::value;
     constexpr KeyT SENT = ~(KeyT)0;
     constexpr u32 FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     KeyT *keys = reinterpret_cast<KeyT *>(smemRaw);
-    T *vals = reinterpret_cast<T *>(smemRaw + L::KEY_BYTES);
-    u32 *sIncl = reinterpret_cast<u32 *>(smemRaw + L::KEY_BYTES + L::VAL_BYTES);
+    T *vals = reinterpret_cast<T *>(smemRaw + L::key_bytes(WARPS));
+    u32 *sIncl = reinterpret_cast<u32 *>(smemRaw + L::key_bytes(WARPS) + L::val_bytes(WARPS));
     u32 *sBs = sIncl + THREADS;
     T *sAv = reinterpret_cast<T *>(sBs + THREADS);
-    unsigned short *sTab = reinterpret_cast<unsigned short *>(smemRaw + L::KEY_BYTES + L::VAL_BYTES + L::BATCH_BYTES);
+    unsigned short *sTab = reinterpret_cast<unsigned short *>(smemRaw + L::key_bytes(WARPS) + L::val_bytes(WARPS) + L::batch_bytes(WARPS));
     __shared__ u32 sWarp[32];
-    __shared__ KeyT sLast[WARPS];
+    __shared__ KeyT sLast[WMAX];
 
     const u32 tid = threadIdx.x;
     const u32 l = tid & 31, w = tid >> 5;
@@ -54,7 +57,7 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
     // ---------------------------------------------------------------- gather (flat over the CTA)
     u32 base = 0;
     for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
-        const u32 nb = min((u32)THREADS, aEnd - ab);
+        const u32 nb = min(THREADS, aEnd - ab);
         u32 bs = 0, len = 0;
         if (tid < nb) {
             const u32 k = __ldg(aCi + ab + tid);
@@ -73,8 +76,8 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
         __syncthreads();
         u32 warpBase = 0, total = 0;
 #pragma unroll
-        for (int i = 0; i < WARPS; ++i) {
-            const u32 s = sWarp[i];
+        for (int i = 0; i < WMAX; ++i) {
+            const u32 s = i < WARPS ? sWarp[i] : 0u;
             if (i < (int)w) warpBase += s;
             total += s;
         }
@@ -139,7 +142,7 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
     // in-warp half cleaners keeps the kernel inside the instruction cache (a fully unrolled 1024-key
     // network stalls ~60 % of its issue slots on instruction fetch, profiles/r1_icache.md).
 #pragma unroll 1
-    for (int k = 2 * WN; k <= N; k <<= 1) {
+    for (int k = 2 * WN; k <= NPOW2; k <<= 1) {
         // mirrored stage (encoded as j == k), then cross-warp half cleaners j = k/4 ... WN
 #pragma unroll 1
         for (int j = k; j >= WN; j >>= 1) {
@@ -152,11 +155,15 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
             __syncthreads();
             const u32 x = (j == k) ? (u32)(k - 1) : (u32)j;
             const bool lower = (j == k) ? ((w & (k / (2 * WN))) == 0) : ((w & (j / WN)) == 0);
+            // partner warp (same for all registers of a lane: x flips whole-warp bits, and for the mirror
+            // also the in-warp bits); a virtual partner holds +inf and always has the higher index
+            if ((((myBase) ^ x) / WN) < (u32)WARPS) {
 #pragma unroll
-            for (int r = 0; r < E; ++r) {
-                const u32 pidx = (myBase + r) ^ x;
-                const KeyT o = keys[pidx + (pidx >> 5)];
-                reg[r] = lower ? key_min(reg[r], o) : key_max(reg[r], o);
+                for (int r = 0; r < E; ++r) {
+                    const u32 pidx = (myBase + r) ^ x;
+                    const KeyT o = keys[pidx + (pidx >> 5)];
+                    reg[r] = lower ? key_min(reg[r], o) : key_max(reg[r], o);
+                }
             }
             __syncthreads();
         }
@@ -183,7 +190,6 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
         __syncthreads();
         if (tid == 0) {
             u32 t = 0;
-#pragma unroll
             for (int i = 0; i < WARPS; ++i) t += sWarp[i];
             cRp[row] = t;
         }
@@ -213,9 +219,7 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
         if (l == 0) sWarp[w] = heads;
         __syncthreads();
         u32 running = 0;
-#pragma unroll
-        for (int i = 0; i < WARPS; ++i)
-            if (i < (int)w) running += sWarp[i];
+        for (int i = 0; i < (int)w; ++i) running += sWarp[i];
         const u32 cBase = cRp[row];
         // pass 2: emit
         for (u32 i0 = segBeg; i0 < segEnd; i0 += 32) {
@@ -245,17 +249,21 @@ k_sort_rows_cta(const u32 *__restrict__ perm, const u32 count, const u32 *__rest
     }
 }
 
-template <int WARPS, int E, typename KeyT, typename T, bool NUMERIC>
-void launch_sort_rows_cta(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
+template <int WMAX, int E, typename KeyT, typename T, bool NUMERIC>
+void launch_sort_rows_cta(const LaunchCtx &lc, int warps, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                           const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, u32 *cRp,
                           u32 *cCi, T *cV)
 {
-    using L = CtaSortLayout<WARPS, E, KeyT, T, NUMERIC>;
-    auto kern = k_sort_rows_cta<WARPS, E, KeyT, T, NUMERIC>;
-    if (L::SMEM > 48 * 1024)
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
-    kern<<<count, L::THREADS, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV);
+    using L = CtaSortLayout<E, KeyT, T, NUMERIC>;
+    auto kern = k_sort_rows_cta<WMAX, E, KeyT, T, NUMERIC>;
+    const size_t smem = L::smem(warps);
+    if (L::smem(WMAX) > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem(WMAX));
+    kern<<<count, warps * 32, smem, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV);
     ++*lc.launches;
 }
+
+// CTA sort class index (0..14) -> warps (2..16) and the power-of-two network size
+inline int cta_class_warps(int ctaClass) { return ctaClass + 2; }
 
 }  // namespace sb

@@ -19,12 +19,12 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
         else                                                                                                 \
             launch_sort_rows<G, E, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
     } while (0)
-#define SB_NUM_CTA(W)                                                                                        \
+#define SB_NUM_CTA(WMAX)                                                                                     \
     do {                                                                                                     \
         if (wideKeys)                                                                                        \
-            launch_sort_rows_cta<W, 16, u64, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+            launch_sort_rows_cta<WMAX, 16, u64, T, true>(lc, warps, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
         else                                                                                                 \
-            launch_sort_rows_cta<W, 16, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+            launch_sort_rows_cta<WMAX, 16, u32, T, true>(lc, warps, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
     } while (0)
     switch (sortClass) {
         case 0: SB_NUM(4, 1); break;
@@ -35,11 +35,14 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
         case 5: SB_NUM(32, 4); break;
         case 6: SB_NUM(32, 8); break;
         case 7: SB_NUM(32, 16); break;
-        case 8: SB_NUM_CTA(2); break;
-        case 9: SB_NUM_CTA(4); break;
-        case 10: SB_NUM_CTA(8); break;
-        case 11: SB_NUM_CTA(16); break;
-        default: break;
+        default: {
+            const int warps = cta_class_warps(sortClass - NUM_WARP_SORT);
+            if (warps <= 2) SB_NUM_CTA(2);
+            else if (warps <= 4) SB_NUM_CTA(4);
+            else if (warps <= 8) SB_NUM_CTA(8);
+            else SB_NUM_CTA(16);
+            break;
+        }
     }
 #undef SB_NUM
 #undef SB_NUM_CTA

@@ -88,8 +88,10 @@ def test_class_boundaries(ctx):
     A, B = _rows_with_products(targets, cols=1 << 18)
     got, st = check_case(ctx, A, B, what="class boundaries")
     assert ndense(st) >= 3
-    for name in ("sort1024", "sort2048", "sort4096", "sort8192"):
-        assert st["class_rows"][name] >= 3, name
+    # CTA classes step by 512 products (2..16 warps): b-1 and b fall in sort{b}, b+1 in sort{b+512}
+    for name in ("sort1024", "sort1536", "sort2048", "sort2560", "sort4096", "sort4608", "sort8192"):
+        assert st["class_rows"][name] >= 1, name
+    assert sum(st["class_rows"][f"sort{512 * w}"] for w in range(2, 17)) >= 11
 
 
 def test_empty_rows_and_empty_b_rows(ctx):
