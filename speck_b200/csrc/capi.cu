@@ -65,6 +65,7 @@ struct speck_ctx {
     size_t hostOutCap[3] = {};
     speck_csr hostC = {};     // device C kept across *_host calls (reuse rules)
     u32 sortMax = SORT_MAX_PRODUCTS;
+    bool rankPath = true;     // rows of 513..8192 products: rank classes instead of the CTA sort classes
     u32 launches = 0;
     speck_stats stats = {};
 };
@@ -134,7 +135,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // CTA-level sort classes (> 1024 products) are used only while (col << log2 N) fits a u32 key;
     // wider matrices send those rows to the bitmap path instead of sorting u64 keys.
     u32 sortMax = c->sortMax;
-    if (sortMax > 1024) {  // largest power-of-two network whose keys fit 32 bits: cols * N <= 2^32
+    const bool useRank = c->rankPath && colsB <= RANK_EXTENT_LIMIT;  // rank classes have no key-width limit
+    if (sortMax > 1024 && !useRank) {  // largest power-of-two network whose keys fit 32 bits: cols * N <= 2^32
         u32 fit = 8192;
         while (fit > 1024 && ((u64)colsB * fit) > (1ull << 32)) fit >>= 1;
         if (sortMax > fit) sortMax = fit;
@@ -200,7 +202,11 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        launch_sort_symbolic(ls, sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, cRp);
+        if (useRank && sc >= NUM_WARP_SORT)
+            launch_rank_symbolic(ls, sc - NUM_WARP_SORT, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps,
+                                 rowMin, rowMax, cRp);
+        else
+            launch_sort_symbolic(ls, sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, cRp);
     }
     join_streams(c);
     cudaEventRecord(c->evStage[2], c->main);
@@ -255,8 +261,12 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         }
         const bool wide = ((u64)colsB * npow2) > (1ull << 32);
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
-                               cRp, cCi, cV);
+        if (useRank && sc >= NUM_WARP_SORT)
+            launch_rank_numeric<T>(ls, sc - NUM_WARP_SORT, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV,
+                                   rowOps, rowMin, rowMax, cRp, cCi, cV);
+        else
+            launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
+                                   cRp, cCi, cV);
     }
     {
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
@@ -573,6 +583,10 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         if (value < 4 || value > (long long)SORT_MAX_PRODUCTS || ((value & (value - 1)) && value % 512))
             return fail(SPECK_ERR_INVALID, "sort_max must be a power of two or a multiple of 512 in [4, %u]", SORT_MAX_PRODUCTS);
         c->sortMax = (u32)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "rank_path")) {
+        c->rankPath = value != 0;
         return SPECK_OK;
     }
     if (!strcmp(key, "release_workspace")) {

@@ -26,13 +26,15 @@ def test_uniform_random(ctx, n, d, seed):
     check_case(ctx, M.uniform_random(n, n, d, seed), what=f"uniform {n} {d}")
 
 
-@pytest.fixture(params=[8192, 1024, 64])
+@pytest.fixture(params=[(8192, 1), (8192, 0), (1024, 1), (64, 1)], ids=["8192-rank", "8192-sort", "1024", "64"])
 def sort_max(ctx, request):
-    """Run a case with the sort/bitmap switch at several places so that every row class
-    (lane-group sort, CTA sort, bitmap) sees the same inputs."""
-    ctx.set_option("sort_max", request.param)
-    yield request.param
+    """Run a case with the sort/bitmap switch at several places, and with the rank classes on and
+    off, so that every row class (lane-group sort, rank, CTA sort, bitmap) sees the same inputs."""
+    ctx.set_option("sort_max", request.param[0])
+    ctx.set_option("rank_path", request.param[1])
+    yield request.param[0]
     ctx.set_option("sort_max", 8192)
+    ctx.set_option("rank_path", 1)
 
 
 @pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16), (15, 16)])
@@ -248,3 +250,38 @@ def test_sort_max_option_routes_more_rows_to_dense(ctx):
         assert st["class_rows"]["sort128"] == 0 and ndense(st) > 0
     finally:
         ctx.set_option("sort_max", 8192)
+
+
+def test_rank_class_many_short_b_rows(ctx):
+    """rank classes: A rows far longer than the CTA (several gather batches), B rows of length 0..3,
+    so products per A entry are tiny and the owner table changes entry almost every product."""
+    rng = np.random.default_rng(31)
+    nb, cols = 6000, 1 << 18
+    blen = rng.integers(0, 4, nb)
+    br = np.repeat(np.arange(nb), blen)
+    B = M.from_coo(nb, cols, br, rng.integers(0, cols, br.size), seed=32)
+    ar, ac = [], []
+    for i, alen in enumerate([700, 1500, 2500, 4000, 5000]):
+        ar += [i] * alen
+        ac += list(rng.choice(nb, alen, replace=False))
+    A = M.from_coo(5, nb, ar, ac, seed=33)
+    got, st = check_case(ctx, A, B, what="rank many short B rows")
+    assert sum(st["class_rows"][f"sort{512 * w}"] for w in range(2, 17)) == 5
+
+
+def test_rank_class_duplicates_over_wide_extent(ctx):
+    """rank classes with heavy folding: every B row draws from the same 300 columns spread over the
+    whole 2^20 extent (extent > 4 * products, so the rows are not taken by the bitmap path)."""
+    rng = np.random.default_rng(34)
+    nb, cols = 400, 1 << 20
+    pool = np.unique(np.concatenate([[0, cols - 1], rng.integers(0, cols, 300)]))
+    br, bc = [], []
+    for k in range(nb):
+        cs = rng.choice(pool, 40, replace=False)
+        br += [k] * 40
+        bc += list(cs)
+    B = M.from_coo(nb, cols, br, bc, seed=35)
+    A = M.uniform_random(64, nb, 60, seed=36)   # ~2400 products per row, <= 302 distinct columns
+    got, st = check_case(ctx, A, B, what="rank duplicates")
+    assert st["products"] > 5 * st["nnz_c"]
+    assert sum(st["class_rows"][f"sort{512 * w}"] for w in range(2, 17)) > 32
