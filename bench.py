@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true",
                     help="skip timing the reference spECK CUDA build (oracle/_ref) on the same GPU")
     ap.add_argument("--sort-max", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +242,9 @@ def main():
     ctx = api.Context(local_rank)
     if args.sort_max:
         ctx.set_option("sort_max", args.sort_max)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 
     # ---------------- setup (untimed): A_r on every rank, B on rank 0 -> NCCL broadcast
     A = load_workload(args.workload, args.seed + rank)

@@ -182,6 +182,10 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     binStart[0] = 0;
     for (int b = 0; b < NUM_BINS; ++b) binStart[b + 1] = binStart[b] + s1.binCount[b];
 
+    // first bin of each rank launch group: CTA class c holds rows of <= 512 * (c + 2) products
+    const int cta0 = BIN_SORT0 + NUM_WARP_SORT;
+    const int rankGroupFirst[5] = {cta0, cta0 + 1, cta0 + 3, cta0 + 7, cta0 + NUM_CTA_SORT};
+
     // bitmaps of the local-dense rows are kept from the symbolic to the numeric phase (2 KB per row)
     u32 *bitmapStore = nullptr;
     {
@@ -198,15 +202,21 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         launch_dense_symbolic(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[loc], aRp,
                               aCi, bRp, bCi, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp);
     }
-    for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
+    // rank classes: the CTA sort bins grouped by launch shape (products <= 8192 / 4096 / 2048 / 1024)
+    if (useRank) {
+        for (int g = 3; g >= 0; --g) {
+            const int b0 = rankGroupFirst[g], b1 = rankGroupFirst[g + 1];
+            const u32 cnt = binStart[b1] - binStart[b0];
+            if (!cnt) continue;
+            LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+            launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp);
+        }
+    }
+    for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        if (useRank && sc >= NUM_WARP_SORT)
-            launch_rank_symbolic(ls, sc - NUM_WARP_SORT, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps,
-                                 rowMin, rowMax, cRp);
-        else
-            launch_sort_symbolic(ls, sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, cRp);
+        launch_sort_symbolic(ls, sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, cRp);
     }
     join_streams(c);
     cudaEventRecord(c->evStage[2], c->main);
@@ -251,7 +261,17 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         launch_dense_numeric<T>(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[2 + loc],
                                 aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV);
     }
-    for (int sc = NUM_SORT - 1; sc >= 0; --sc) {
+    if (useRank) {
+        for (int g = 3; g >= 0; --g) {
+            const int b0 = rankGroupFirst[g], b1 = rankGroupFirst[g + 1];
+            const u32 cnt = binStart[b1] - binStart[b0];
+            if (!cnt) continue;
+            LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+            launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
+                                   rowMax, cRp, cCi, cV);
+        }
+    }
+    for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
         u32 npow2 = 4u << sc;  // lane-group classes
@@ -261,11 +281,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         }
         const bool wide = ((u64)colsB * npow2) > (1ull << 32);
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        if (useRank && sc >= NUM_WARP_SORT)
-            launch_rank_numeric<T>(ls, sc - NUM_WARP_SORT, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV,
-                                   rowOps, rowMin, rowMax, cRp, cCi, cV);
-        else
-            launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
+        launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
                                    cRp, cCi, cV);
     }
     {
@@ -583,6 +599,10 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         if (value < 4 || value > (long long)SORT_MAX_PRODUCTS || ((value & (value - 1)) && value % 512))
             return fail(SPECK_ERR_INVALID, "sort_max must be a power of two or a multiple of 512 in [4, %u]", SORT_MAX_PRODUCTS);
         c->sortMax = (u32)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "rank_slots")) {
+        set_rank_slots((int)value);
         return SPECK_OK;
     }
     if (!strcmp(key, "rank_path")) {

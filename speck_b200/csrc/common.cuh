@@ -95,11 +95,12 @@ void launch_direct_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, cons
 
 // rank classes (rank_cta.cuh): the CTA sort classes' rows when cols(B) <= RANK_EXTENT_LIMIT
 constexpr u32 RANK_EXTENT_LIMIT = 1u << 20;
-void launch_rank_symbolic(const LaunchCtx &lc, int ctaClass, const u32 *perm, u32 count, const u32 *aRp,
+void set_rank_slots(int e);   // experiment switch: 4 or 8 product slots per thread
+void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                           const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, const u32 *rowMin,
                           const u32 *rowMax, u32 *rowNnz);
 template <typename T>
-void launch_rank_numeric(const LaunchCtx &lc, int ctaClass, const u32 *perm, u32 count, const u32 *aRp,
+void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
                          const u32 *rowOps, const u32 *rowMin, const u32 *rowMax, const u32 *cRp, u32 *cCi, T *cV);
 

@@ -27,11 +27,13 @@ namespace sb {
 constexpr int RANK_TOP_WORDS = 1024;
 constexpr u32 RANK_MAX_EXTENT = 1u << 20;   // RANK_TOP_WORDS * 32 * 32 columns
 
-// exclusive scan of one u32 per thread over a CTA of blockDim.x threads (multiple of 32);
-// sWarp: 33 words.  Contains two barriers; *total = block sum.
+// exclusive scan of one u32 per thread over a CTA of THREADS threads; sWarp: 33 words.
+// Contains two barriers; *total = block sum.
+template <int THREADS>
 __device__ __forceinline__ u32 cta_exclusive_scan(u32 v, u32 *sWarp, u32 *total)
 {
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr u32 NW = THREADS / 32;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -41,57 +43,65 @@ __device__ __forceinline__ u32 cta_exclusive_scan(u32 v, u32 *sWarp, u32 *total)
     if (lane == 31) sWarp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const u32 wv = lane < nw ? sWarp[lane] : 0u;
+        const u32 wv = lane < NW ? sWarp[lane] : 0u;
         u32 winc = wv;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int d = 1; d < (int)NW; d <<= 1) {
             const u32 t = __shfl_up_sync(0xffffffffu, winc, d);
             if (lane >= (u32)d) winc += t;
         }
-        sWarp[lane] = winc - wv;
-        if (lane == 31) sWarp[32] = winc;
+        if (lane < NW) sWarp[lane] = winc - wv;
+        if (lane == NW - 1) sWarp[32] = winc;
     }
     __syncthreads();
     *total = sWarp[32];
     return sWarp[warp] + incl - v;
 }
 
-// Shared memory of a CTA of `threads` threads (cap = threads * E product slots), 16-byte aligned pieces:
-//   outVal[cap] T | sAv[threads] T | top[1024] | topPre[1024] u16 | leaf[cap] | leafPre[cap] u16 |
-//   leafId[cap] u16 | sIncl[threads] | sBs[threads] | sTab[cap/32] u16 | outCol[cap] (numeric, aliased onto
+// Shared memory of a CTA of THREADS threads (CAP = THREADS * E product slots), 16-byte aligned pieces, all
+// offsets compile-time:
+//   outVal[CAP] T | sAv[THREADS] T | top[1024] | topPre[1024] u16 | leaf[CAP] | leafPre[CAP] u16 |
+//   leafId[CAP] u16 | sIncl[THREADS] | sBs[THREADS] | sTab[CAP/32] u16 | outCol[CAP] (numeric; aliased onto
 //   top/topPre when it fits: both are dead once the leaf words are filled)
-template <int E, typename T, bool NUMERIC>
+template <int THREADS, int E, typename T, bool NUMERIC>
 struct RankLayout {
-    __host__ __device__ static constexpr size_t al(size_t b) { return (b + 15) / 16 * 16; }
-    __host__ __device__ static bool col_aliased(int threads) { return (size_t)threads * E * 4 <= RANK_TOP_WORDS * 6; }
-    __host__ __device__ static size_t smem(int threads)
-    {
-        const size_t cap = (size_t)threads * E;
-        size_t b = RANK_TOP_WORDS * (4 + 2);
-        b += al(cap * 4) + al(cap * 2) + al(threads * 4) * 2 + al(cap / 32 * 2);
-        if (NUMERIC) b += al(cap * 2) + al(cap * sizeof(T)) + al(threads * sizeof(T)) + (col_aliased(threads) ? 0 : cap * 4);
-        return b;
-    }
+    static constexpr size_t al(size_t b) { return (b + 15) / 16 * 16; }
+    static constexpr size_t CAP = (size_t)THREADS * E;
+    static constexpr bool COL_ALIASED = CAP * 4 <= RANK_TOP_WORDS * 6;
+    static constexpr size_t OUTVAL = 0;
+    static constexpr size_t SAV = OUTVAL + (NUMERIC ? al(CAP * sizeof(T)) : 0);
+    static constexpr size_t TOP = SAV + (NUMERIC ? al(THREADS * sizeof(T)) : 0);
+    static constexpr size_t TOPPRE = TOP + RANK_TOP_WORDS * 4;
+    static constexpr size_t LEAF = TOPPRE + RANK_TOP_WORDS * 2;
+    static constexpr size_t LEAFPRE = LEAF + al(CAP * 4);
+    static constexpr size_t LEAFID = LEAFPRE + al(CAP * 2);
+    static constexpr size_t SINCL = LEAFID + (NUMERIC ? al(CAP * 2) : 0);
+    static constexpr size_t SBS = SINCL + al(THREADS * 4);
+    static constexpr size_t STAB = SBS + al(THREADS * 4);
+    static constexpr size_t OUTCOL = (NUMERIC && COL_ALIASED) ? TOP : STAB + al(CAP / 32 * 2);
+    static constexpr size_t SMEM = STAB + al(CAP / 32 * 2) + ((NUMERIC && !COL_ALIASED) ? CAP * 4 : 0);
 };
 
-// popcount prefix of a level: words[0..n) (n padded to a multiple of 4 by the caller, padding words are 0)
+// popcount prefix of a level: words[0..n) (padded with zero words to a multiple of 4 by the caller)
 // -> pre[j] = number of set bits in words[0..j), returns the total.  Threads own consecutive groups of four
 // words (one 16-byte load, one 8-byte store of four packed u16 prefixes).
-template <bool WRITE_PREFIX>
+template <int THREADS, bool WRITE_PREFIX>
 __device__ __forceinline__ u32 rank_scan_level(const u32 *bits, unsigned short *pre, u32 words, u32 *sWarp)
 {
-    const u32 THREADS = blockDim.x, tid = threadIdx.x;
+    const u32 tid = threadIdx.x;
     const u32 groups = (words + 3) >> 2;
     const u32 per = (groups + THREADS - 1) / THREADS;
     const u32 g0 = min(groups, tid * per), g1 = min(groups, g0 + per);
     u32 s = 0;
+#pragma unroll 1
     for (u32 g = g0; g < g1; ++g) {
         const uint4 v = reinterpret_cast<const uint4 *>(bits)[g];
         s += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
     }
     u32 tot;
-    u32 run = cta_exclusive_scan(s, sWarp, &tot);
+    u32 run = cta_exclusive_scan<THREADS>(s, sWarp, &tot);
     if (WRITE_PREFIX) {
+#pragma unroll 1
         for (u32 g = g0; g < g1; ++g) {
             const uint4 v = reinterpret_cast<const uint4 *>(bits)[g];
             const u32 p1 = run + __popc(v.x), p2 = p1 + __popc(v.y), p3 = p2 + __popc(v.z);
@@ -102,31 +112,27 @@ __device__ __forceinline__ u32 rank_scan_level(const u32 *bits, unsigned short *
     return tot;
 }
 
-template <int E, int MAXT, typename T, bool NUMERIC>
-__global__ void __launch_bounds__(MAXT)
+template <int THREADS, int E, typename T, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS)
 k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32 *__restrict__ aCi,
             const T *__restrict__ aV, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
             const T *__restrict__ bV, const u32 *__restrict__ rowOps, const u32 *__restrict__ rowMin,
             const u32 *__restrict__ rowMax, u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV)
 {
-    using L = RankLayout<E, T, NUMERIC>;
+    using L = RankLayout<THREADS, E, T, NUMERIC>;
     constexpr u32 NONE = 0xffffffffu;
-    const u32 THREADS = blockDim.x;
-    const u32 CAP = THREADS * E;
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    unsigned char *sp = smemRaw;
-    auto carve = [&](size_t bytes) { unsigned char *p = sp; sp += L::al(bytes); return p; };
-    T *outVal = reinterpret_cast<T *>(carve(NUMERIC ? CAP * sizeof(T) : 0));
-    T *sAv = reinterpret_cast<T *>(carve(NUMERIC ? THREADS * sizeof(T) : 0));
-    u32 *top = reinterpret_cast<u32 *>(carve(RANK_TOP_WORDS * 4));
-    unsigned short *topPre = reinterpret_cast<unsigned short *>(carve(RANK_TOP_WORDS * 2));
-    u32 *leaf = reinterpret_cast<u32 *>(carve(CAP * 4));
-    unsigned short *leafPre = reinterpret_cast<unsigned short *>(carve(CAP * 2));
-    unsigned short *leafId = reinterpret_cast<unsigned short *>(carve(NUMERIC ? CAP * 2 : 0));
-    u32 *sIncl = reinterpret_cast<u32 *>(carve(THREADS * 4));
-    u32 *sBs = reinterpret_cast<u32 *>(carve(THREADS * 4));
-    unsigned short *sTab = reinterpret_cast<unsigned short *>(carve(CAP / 32 * 2));
-    u32 *outCol = L::col_aliased(THREADS) ? top : reinterpret_cast<u32 *>(sp);
+    T *outVal = reinterpret_cast<T *>(smemRaw + L::OUTVAL);
+    T *sAv = reinterpret_cast<T *>(smemRaw + L::SAV);
+    u32 *top = reinterpret_cast<u32 *>(smemRaw + L::TOP);
+    unsigned short *topPre = reinterpret_cast<unsigned short *>(smemRaw + L::TOPPRE);
+    u32 *leaf = reinterpret_cast<u32 *>(smemRaw + L::LEAF);
+    unsigned short *leafPre = reinterpret_cast<unsigned short *>(smemRaw + L::LEAFPRE);
+    unsigned short *leafId = reinterpret_cast<unsigned short *>(smemRaw + L::LEAFID);
+    u32 *sIncl = reinterpret_cast<u32 *>(smemRaw + L::SINCL);
+    u32 *sBs = reinterpret_cast<u32 *>(smemRaw + L::SBS);
+    unsigned short *sTab = reinterpret_cast<unsigned short *>(smemRaw + L::STAB);
+    u32 *outCol = reinterpret_cast<u32 *>(smemRaw + L::OUTCOL);
     __shared__ u32 sWarp[33];
 
     const u32 tid = threadIdx.x;
@@ -135,6 +141,12 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
     const u32 cmin = rowMin[row];
     const u32 topWords = ((rowMax[row] - cmin) >> 10) + 1;   // <= RANK_TOP_WORDS: the host checks cols(B)
+    u32 cBase = 0, nnzRow = 0;
+    if (NUMERIC) {
+        cBase = cRp[row];
+        nnzRow = cRp[row + 1] - cBase;
+    }
+#pragma unroll 1
     for (u32 j = tid; j < (topWords + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(top)[j] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
@@ -146,8 +158,9 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
 #pragma unroll
     for (int i = 0; i < E; ++i) { col[i] = NONE; prod[i] = (T)0; }
     u32 base = 0;
+#pragma unroll 1
     for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
-        const u32 nb = min(THREADS, aEnd - ab);
+        const u32 nb = min((u32)THREADS, aEnd - ab);
         u32 bs = 0, len = 0;
         if (tid < nb) {
             const u32 k = __ldg(aCi + ab + tid);
@@ -156,7 +169,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
             if (NUMERIC) sAv[tid] = __ldg(aV + ab + tid);
         }
         u32 total;
-        const u32 excl = cta_exclusive_scan(len, sWarp, &total);
+        const u32 excl = cta_exclusive_scan<THREADS>(len, sWarp, &total);
         sIncl[tid] = excl + len;
         sBs[tid] = bs - excl;  // q = sBs[owner] + p
         if (len) {             // owner table: sTab[b] = entry owning product 32*b of this batch
@@ -164,19 +177,20 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
             for (u32 b = (excl + 31) >> 5; b <= bLast; ++b) sTab[b] = (unsigned short)tid;
         }
         __syncthreads();
+        constexpr int GU = E < 4 ? E : 4;   // products per thread in flight
 #pragma unroll
-        for (int i0 = 0; i0 < E; i0 += 4) {
-            if ((u32)i0 * THREADS >= base + total) break;          // CTA-uniform
-            if ((u32)(i0 + 4) * THREADS <= base) continue;         // CTA-uniform (earlier batch)
-            u32 q[4], cc[4];
-            T av[4], bv[4];
+        for (int i0 = 0; i0 < E; i0 += GU) {
+            if ((u32)i0 * THREADS >= base + total) break;           // CTA-uniform
+            if ((u32)(i0 + GU) * THREADS <= base) continue;         // CTA-uniform (earlier batch)
+            u32 q[GU], cc[GU];
+            T av[GU], bv[GU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GU; ++u) {
                 const u32 gp = (u32)(i0 + u) * THREADS + tid;
                 const u32 p = gp - base;
                 q[u] = NONE;
                 av[u] = (T)0;
-                if (gp >= base && p < total) {
+                if (p < total) {   // gp < base wraps p beyond any total
                     u32 lo = sTab[p >> 5];
                     while (sIncl[lo] <= p) ++lo;
                     q[u] = sBs[lo] + p;
@@ -184,12 +198,14 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GU; ++u) {
+                if ((u32)(i0 + u) * THREADS >= base + total) break;
                 cc[u] = q[u] != NONE ? __ldg(bCi + q[u]) : 0u;
                 bv[u] = (NUMERIC && q[u] != NONE) ? __ldg(bV + q[u]) : (T)0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GU; ++u) {
+                if ((u32)(i0 + u) * THREADS >= base + total) break;
                 if (q[u] != NONE) {
                     const u32 c = cc[u] - cmin;
                     col[i0 + u] = c;
@@ -203,7 +219,8 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     }
 
     // ---------------------------------------------------------------- leaf words of the touched chunks
-    const u32 leaves = rank_scan_level<true>(top, topPre, topWords, sWarp);
+    const u32 leaves = rank_scan_level<THREADS, true>(top, topPre, topWords, sWarp);
+#pragma unroll 1
     for (u32 j = tid; j < (leaves + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(leaf)[j] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     u32 dup = 0;   // bit i: slot i is not the first product of its column
@@ -226,11 +243,11 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     __syncthreads();
 
     if (!NUMERIC) {
-        const u32 distinct = rank_scan_level<false>(leaf, nullptr, leaves, sWarp);
+        const u32 distinct = rank_scan_level<THREADS, false>(leaf, nullptr, leaves, sWarp);
         if (tid == 0) cRp[row] = distinct;
         return;
     } else {
-        rank_scan_level<true>(leaf, leafPre, leaves, sWarp);
+        rank_scan_level<THREADS, true>(leaf, leafPre, leaves, sWarp);
         __syncthreads();
         // ------------------------------------------------------------ first product of a column: plain stores
 #pragma unroll
@@ -253,8 +270,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
                 if ((dup >> i) & 1u) atomicAdd(&outVal[col[i]], prod[i]);
             __syncthreads();
         }
-        const u32 cBase = cRp[row];
-        const u32 nnzRow = cRp[row + 1] - cBase;
+#pragma unroll 1
         for (u32 j = tid; j < nnzRow; j += THREADS) {
             cCi[cBase + j] = outCol[j];
             cV[cBase + j] = outVal[j];
@@ -262,18 +278,16 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     }
 }
 
-// threads = products capacity / E, a multiple of 32, <= MAXT
-template <int E, int MAXT, typename T, bool NUMERIC>
-void launch_rank_rows(const LaunchCtx &lc, int threads, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
+template <int THREADS, int E, typename T, bool NUMERIC>
+void launch_rank_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                       const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, const u32 *rowMin,
                       const u32 *rowMax, u32 *cRp, u32 *cCi, T *cV)
 {
-    using L = RankLayout<E, T, NUMERIC>;
-    auto kern = k_rank_rows<E, MAXT, T, NUMERIC>;
-    const size_t smem = L::smem(threads);
-    if (L::smem(MAXT) > 48 * 1024)
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem(MAXT));
-    kern<<<count, threads, smem, lc.stream>>>(perm, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax, cRp, cCi, cV);
+    using L = RankLayout<THREADS, E, T, NUMERIC>;
+    auto kern = k_rank_rows<THREADS, E, T, NUMERIC>;
+    if (L::SMEM > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+    kern<<<count, THREADS, L::SMEM, lc.stream>>>(perm, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax, cRp, cCi, cV);
     ++*lc.launches;
 }
 
