@@ -59,13 +59,14 @@ struct speck_ctx {
     cudaEvent_t evStage[6] = {};
     Scalars *dSc = nullptr;
     Scalars *hSc = nullptr;  // pinned
-    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore;
+    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore, mapLen, mapBase, rankMap, aSeg, desc;
     DevBuf stage[6];          // device staging of the *_host entry points (A: rp, ci, v; B: rp, ci, v)
     void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
     size_t hostOutCap[3] = {};
     speck_csr hostC = {};     // device C kept across *_host calls (reuse rules)
     u32 sortMax = SORT_MAX_PRODUCTS;
     bool rankPath = true;     // rows of 513..8192 products: rank classes instead of the CTA sort classes
+    bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
     u32 launches = 0;
     speck_stats stats = {};
 };
@@ -93,6 +94,17 @@ void release(DevBuf &b)
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
+}
+
+// sort classes: u32 keys while (col << log2 N) fits, N = power-of-two size of the class's sorting network
+bool sort_keys_wide(int sc, u32 colsB)
+{
+    u32 npow2 = 4u << sc;  // lane-group classes
+    if (sc >= NUM_WARP_SORT) {
+        npow2 = 1024;
+        while (npow2 < 512u * (u32)(sc - NUM_WARP_SORT + 2)) npow2 <<= 1;
+    }
+    return ((u64)colsB * npow2) > (1ull << 32);
 }
 
 void fork_streams(speck_ctx *c)
@@ -150,6 +162,13 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     if ((rc = ensure(c->rowMin, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->rowMax, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->tileState, scan_tile_state_bytes(rows + 1)))) return rc;
+    const bool wantMap = c->rankMapOn;
+    if (wantMap) {
+        if ((rc = ensure(c->mapLen, (size_t)(rows + 1) * 4))) return rc;
+        if ((rc = ensure(c->mapBase, (size_t)(rows + 1) * 8))) return rc;
+        if ((rc = ensure(c->aSeg, (size_t)A->nnz * sizeof(uint2)))) return rc;
+        if ((rc = ensure(c->desc, (size_t)rows * sizeof(RowDesc)))) return rc;
+    }
     u32 *cRp = C->row_offsets;
     if (!(C->rows == A->rows && cRp != nullptr)) {
         if (cRp) cudaFree(cRp);
@@ -163,8 +182,11 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
 
     // ---- analysis + binning
-    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax);
-    launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax);
+    launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
+                   wantMap ? (uint2 *)c->aSeg.p : nullptr);
+    launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (u32 *)c->mapLen.p : nullptr,
+                       useRank);
+    if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     cudaEventRecord(c->evStage[1], c->main);
     CU_TRY(cudaStreamSynchronize(c->main));
@@ -192,6 +214,27 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         const size_t need = dense_local_store_bytes(s1.binCount[BIN_DENSE_LOCAL]);
         if (need && need <= ((size_t)8 << 30) && ensure(c->bitmapStore, need) == SPECK_OK) bitmapStore = (u32 *)c->bitmapStore.p;
     }
+    // rank map (2 B per product of the mapped rows): optional -- without it (switched off, or no memory) the
+    // numeric phase recomputes the positions with the self-contained kernels
+    unsigned short *rankMap = nullptr;
+    RowDesc *desc = nullptr;
+    const uint2 *aSeg = nullptr;
+    if (wantMap && s1.mapTotal) {
+        const size_t need = (size_t)s1.mapTotal * 2;
+        bool fits = need <= c->rankMap.cap;
+        if (!fits) {  // grow only while it leaves at least half of the free memory to C
+            size_t freeB = 0, totalB = 0;
+            cudaMemGetInfo(&freeB, &totalB);
+            fits = need < (freeB + c->rankMap.cap) / 2;
+        }
+        if (fits && ensure(c->rankMap, need) == SPECK_OK) {
+            rankMap = (unsigned short *)c->rankMap.p;
+            desc = (RowDesc *)c->desc.p;
+            aSeg = (const uint2 *)c->aSeg.p;
+            // descriptors of all binned rows, perm order (desc + binStart[b] = first row of bin b)
+            launch_build_desc(lc, perm, binStart[NUM_BINS], aRp, rowOps, rowMin, rowMax, (const u64 *)c->mapBase.p, desc);
+        }
+    }
     // ---- symbolic: dense rows first (longest), then the sort classes from large to small
     fork_streams(c);
     int sidx = 0;
@@ -209,14 +252,16 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             const u32 cnt = binStart[b1] - binStart[b0];
             if (!cnt) continue;
             LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-            launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp);
+            launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp,
+                                 desc ? desc + binStart[b0] : nullptr, aSeg, rankMap);
         }
     }
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        launch_sort_symbolic(ls, sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, cRp);
+        launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
+                             rowOps, cRp, desc ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
     }
     join_streams(c);
     cudaEventRecord(c->evStage[2], c->main);
@@ -252,6 +297,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
 
     // ---- numeric
     cudaEventRecord(c->evStage[4], c->main);
+    if (rankMap) launch_desc_numeric(lc, binStart[NUM_BINS], cRp, desc);
     fork_streams(c);
     sidx = 0;
     for (int loc = 0; loc < 2; ++loc) {
@@ -267,22 +313,22 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             const u32 cnt = binStart[b1] - binStart[b0];
             if (!cnt) continue;
             LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-            launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
-                                   rowMax, cRp, cCi, cV);
+            if (rankMap)
+                launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
+            else
+                launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
+                                       rowMax, cRp, cCi, cV);
         }
     }
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
-        u32 npow2 = 4u << sc;  // lane-group classes
-        if (sc >= NUM_WARP_SORT) {
-            npow2 = 1024;
-            while (npow2 < 512u * (u32)(sc - NUM_WARP_SORT + 2)) npow2 <<= 1;
-        }
-        const bool wide = ((u64)colsB * npow2) > (1ull << 32);
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        launch_sort_numeric<T>(ls, sc, wide, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps,
-                                   cRp, cCi, cV);
+        if (rankMap && sc < NUM_WARP_SORT)
+            launch_map_numeric<T>(ls, sc, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
+        else
+            launch_sort_numeric<T>(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV,
+                                   bRp, bCi, bV, rowOps, cRp, cCi, cV);
     }
     {
         LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
@@ -307,7 +353,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     cudaEventElapsedTime(&st.ms_scan, c->evStage[2], c->evStage[3]);
     cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
     cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
-    st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->rowMin.cap + c->rowMax.cap + c->tileState.cap + c->bitmapStore.cap;
+    st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->rowMin.cap + c->rowMax.cap + c->tileState.cap + c->bitmapStore.cap +
+                         c->mapLen.cap + c->mapBase.cap + c->rankMap.cap + c->aSeg.cap + c->desc.cap;
     if (tm) {
         float allocMs = 0.f;
         cudaEventElapsedTime(&allocMs, c->evStage[3], c->evStage[4]);
@@ -457,7 +504,7 @@ int speck_b200_destroy(speck_ctx *c)
     if (!c) return SPECK_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore);
+    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc);
     for (auto &b : c->stage) release(b);
     for (auto &h : c->hostOut) if (h) cudaFreeHost(h);
     if (c->hostC.data) cudaFree(c->hostC.data);
@@ -523,7 +570,7 @@ int speck_b200_row_products(speck_ctx *c, const speck_csr *A, const speck_csr *B
     u32 n = 0;
     LaunchCtx lc{c->main, c->smCount, &n};
     launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, B->col_ids, (u32 *)c->rowOps.p,
-                   (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax);
+                   (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax, nullptr);
     if (dRowOps) CU_TRY(cudaMemcpyAsync(dRowOps, c->rowOps.p, (size_t)rows * 4, cudaMemcpyDeviceToDevice, c->main));
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     CU_TRY(cudaStreamSynchronize(c->main));
@@ -601,8 +648,8 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         c->sortMax = (u32)value;
         return SPECK_OK;
     }
-    if (!strcmp(key, "rank_slots")) {
-        set_rank_slots((int)value);
+    if (!strcmp(key, "rank_map")) {
+        c->rankMapOn = value != 0;
         return SPECK_OK;
     }
     if (!strcmp(key, "rank_path")) {
@@ -612,7 +659,7 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "release_workspace")) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore);
+        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc);
         for (auto &b : c->stage) release(b);
         return SPECK_OK;
     }

@@ -43,8 +43,21 @@ struct Scalars {
     u32 binCount[NUM_BINS];   // rows per bin (written by k_analyze)
     u32 binCursor[NUM_BINS];  // scatter cursors (k_bin_scatter)
     u32 denseCounter[4];      // dynamic row queues of the dense kernels (symbolic/numeric x local/wide)
-    u32 tileCounter;          // dynamic tile ids of the scan
+    u32 tileCounter;          // dynamic tile ids of the row_ptr scan
+    u32 mapTileCounter;       // dynamic tile ids of the rank-map offset scan
+    u64 mapTotal;             // entries of the rank map (products of all mapped rows)
     u32 compareFlag;          // k_compare: 0 = equal
+};
+
+// Row descriptor of the mapped classes, one per binned row in perm order (built once per multiply): a CTA /
+// lane group reads its row's parameters with two 16-byte loads instead of chasing perm -> row -> five arrays.
+struct __align__(16) RowDesc {
+    u32 aBeg, aLen;   // A entries of the row
+    u32 n;            // products of the row
+    u32 row;
+    u32 c0;           // symbolic: smallest column of the row; numeric: first position of the row in C
+    u32 c1;           // symbolic: largest column;              numeric: entries of the row in C
+    u64 mapOff;       // first rank-map entry of the row
 };
 
 struct CsrView {
@@ -74,16 +87,46 @@ struct LaunchCtx {
     u32 *launches;   // incremented per kernel launch
 };
 
+// aSeg (optional, nnz(A) entries): (begin, end) of the B row referenced by every A entry, so that the row
+// kernels need one load level (aSeg) instead of two (A.col_ids -> B.row_offsets)
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
-                    const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax);
+                    const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
+                    uint2 *aSeg);
+// descriptors of perm[0..count): symbolic flavour (c0/c1 = column extent), then switched to the numeric
+// flavour (c0/c1 = position / length in C) once row_offsets are scanned
+void launch_build_desc(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *rowOps,
+                       const u32 *rowMin, const u32 *rowMax, const u64 *mapBase, RowDesc *desc);
+void launch_desc_numeric(const LaunchCtx &lc, u32 count, const u32 *cRp, RowDesc *desc);
+// mapLen (optional, rows + 1 entries): products of the row when its class records a rank map in the symbolic
+// phase (lane-group classes always, CTA classes when mapCta), else 0
 void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
-                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax);
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta);
 void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trailing total slot */,
                  u64 *tileState, Scalars *sc);
+// exclusive scan of in[0..n-1) into 64-bit out[0..n) (out[n-1] = total, also stored in sc->mapTotal)
+void launch_scan_map(const LaunchCtx &lc, const u32 *in, u64 *out, u32 n, u64 *tileState, Scalars *sc);
+
+// Rank map: one u16 per product of a mapped row, written by the symbolic phase at mapBase[row] + (index of the
+// product in the row's flat enumeration: A entries ascending, then B-row order):
+//   bits 0..14 = position of the product's column in the sorted row of C, bit 15 = not the first product of
+//   that column.  The numeric phase then only gathers, multiplies and scatters by rank.
+constexpr u32 MAP_DUP = 0x8000u;
+constexpr u32 MAP_RANK_MASK = 0x7fffu;
 size_t scan_tile_state_bytes(u32 n);
 
-void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, const u32 *perm, u32 count, const u32 *aRp,
-                          const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, u32 *rowNnz);
+// mapBase / rankMap == nullptr: count only; wideKeys as in launch_sort_numeric (needed for the map only)
+void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
+                          const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps,
+                          u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg, unsigned short *rankMap);
+// numeric phase of mapped rows: lane-group classes (sortClass < NUM_WARP_SORT) ...
+template <typename T>
+void launch_map_numeric(const LaunchCtx &lc, int sortClass, const RowDesc *desc, u32 count, const uint2 *aSeg,
+                        const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi, T *cV);
+// ... and CTA classes (rows of <= capProducts products)
+template <typename T>
+void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
+                            const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi,
+                            T *cV);
 template <typename T>
 void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
                          const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi,
@@ -95,10 +138,10 @@ void launch_direct_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, cons
 
 // rank classes (rank_cta.cuh): the CTA sort classes' rows when cols(B) <= RANK_EXTENT_LIMIT
 constexpr u32 RANK_EXTENT_LIMIT = 1u << 20;
-void set_rank_slots(int e);   // experiment switch: 4 or 8 product slots per thread
 void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                           const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, const u32 *rowMin,
-                          const u32 *rowMax, u32 *rowNnz);
+                          const u32 *rowMax, u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg,
+                          unsigned short *rankMap);
 template <typename T>
 void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                                                  const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
                                                  u32 *__restrict__ rowOps, u32 *__restrict__ rowMin,
                                                  u32 *__restrict__ rowMax, u32 *__restrict__ rowNnz, Scalars *sc,
-                                                 u32 sortMax)
+                                                 u32 sortMax, uint2 *__restrict__ aSeg)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
             const u32 k = __ldg(aCi + p);
             const u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
             ops64 += (u64)(be - bs);
+            if (aSeg) aSeg[p] = make_uint2(bs, be);
             if (be > bs) {
                 cmin = min(cmin, __ldg(bCi + bs));
                 cmax = max(cmax, __ldg(bCi + be - 1));
@@ -91,20 +92,21 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 }
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
-                    const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax)
+                    const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
+                    uint2 *aSeg)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
     const int threads = 256;
     if (avg <= 3.0) {
         const u32 grid = (u32)(((u64)rows * 2 + threads - 1) / threads);
-        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax);
+        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg);
     } else if (avg <= 24.0) {
         const u32 grid = (u32)(((u64)rows * 8 + threads - 1) / threads);
-        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax);
+        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg);
     } else {
         const u32 grid = (u32)(((u64)rows * 32 + threads - 1) / threads);
-        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax);
+        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg);
     }
     ++*lc.launches;
 }
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
                                                      const u32 *__restrict__ rowOps,
                                                      const u32 *__restrict__ rowMin,
                                                      const u32 *__restrict__ rowMax, u32 *__restrict__ perm,
-                                                     Scalars *sc, u32 sortMax)
+                                                     Scalars *sc, u32 sortMax, u32 *__restrict__ mapLen,
+                                                     bool mapCta)
 {
     __shared__ u32 sCnt[NUM_BINS];
     __shared__ u32 sBase[NUM_BINS];
@@ -131,6 +134,10 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
         const u32 ops = rowOps[row];
         bin = classify_row(ops, aRp[row + 1] - aRp[row], ops ? rowMax[row] - rowMin[row] + 1u : 0u, sortMax);
         if (bin >= 0) rank = atomicAdd(&sCnt[bin], 1u);
+        if (mapLen) {
+            const bool mapped = bin >= BIN_SORT0 && (bin < BIN_SORT0 + NUM_WARP_SORT || (mapCta && bin < BIN_DENSE_LOCAL));
+            mapLen[row] = mapped ? ops : 0u;
+        }
     }
     __syncthreads();
     if (threadIdx.x < NUM_BINS) {
@@ -144,10 +151,58 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
 }
 
 void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
-                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax)
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta)
 {
     if (rows == 0) return;
-    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, rowMin, rowMax, perm, sc, sortMax);
+    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, rowMin, rowMax, perm, sc, sortMax, mapLen,
+                                                             mapCta);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// Row descriptors of the mapped classes (common.cuh: RowDesc), in perm order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_desc(const u32 *__restrict__ perm, u32 count,
+                                                    const u32 *__restrict__ aRp, const u32 *__restrict__ rowOps,
+                                                    const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax,
+                                                    const u64 *__restrict__ mapBase, RowDesc *__restrict__ desc)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const u32 row = perm[j];
+    RowDesc d;
+    d.aBeg = aRp[row];
+    d.aLen = aRp[row + 1] - d.aBeg;
+    d.n = rowOps[row];
+    d.row = row;
+    d.c0 = rowMin[row];
+    d.c1 = rowMax[row];
+    d.mapOff = mapBase[row];
+    desc[j] = d;
+}
+
+__global__ void __launch_bounds__(256) k_desc_numeric(u32 count, const u32 *__restrict__ cRp, RowDesc *desc)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const u32 row = desc[j].row;
+    const u32 b = cRp[row];
+    desc[j].c0 = b;
+    desc[j].c1 = cRp[row + 1] - b;
+}
+
+void launch_build_desc(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *rowOps,
+                       const u32 *rowMin, const u32 *rowMax, const u64 *mapBase, RowDesc *desc)
+{
+    if (count == 0) return;
+    k_build_desc<<<(count + 255) / 256, 256, 0, lc.stream>>>(perm, count, aRp, rowOps, rowMin, rowMax, mapBase, desc);
+    ++*lc.launches;
+}
+
+void launch_desc_numeric(const LaunchCtx &lc, u32 count, const u32 *cRp, RowDesc *desc)
+{
+    if (count == 0) return;
+    k_desc_numeric<<<(count + 255) / 256, 256, 0, lc.stream>>>(count, cRp, desc);
     ++*lc.launches;
 }
 
@@ -166,13 +221,14 @@ constexpr u64 VALUE_MASK = (1ull << 62) - 1;
 
 size_t scan_tile_state_bytes(u32 n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1) * sizeof(u64); }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(u32 *__restrict__ data, u32 n,
-                                                       volatile u64 *tileState, Scalars *sc)
+template <typename OutT>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const u32 *data, OutT *out, u32 n, volatile u64 *tileState,
+                                                       u32 *tileCounter, u64 *totalOut)
 {
     __shared__ u32 sTile;
     __shared__ u64 sWarpSum[SCAN_THREADS / 32];
     __shared__ u64 sExclusive;
-    if (threadIdx.x == 0) sTile = atomicAdd(&sc->tileCounter, 1u);
+    if (threadIdx.x == 0) sTile = atomicAdd(tileCounter, 1u);
     __syncthreads();
     const u32 tile = sTile;
     const u32 base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
@@ -241,8 +297,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(u32 *__restrict__ data, u
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         const u32 idx = base + i;
-        if (idx < n) data[idx] = (u32)run;
-        if (idx == n - 1) sc->nnzC = run;  // 64-bit total: overflow of the u32 API is detectable
+        if (idx < n) out[idx] = (OutT)run;
+        if (idx == n - 1) *totalOut = run;  // 64-bit total: overflow of the u32 API is detectable
         run += items[i];
     }
 }
@@ -252,7 +308,16 @@ void launch_scan(const LaunchCtx &lc, u32 *data, u32 n, u64 *tileState, Scalars 
     if (n == 0) return;
     const u32 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     cudaMemsetAsync(tileState, 0, (size_t)tiles * sizeof(u64), lc.stream);
-    k_scan<<<tiles, SCAN_THREADS, 0, lc.stream>>>(data, n, tileState, sc);
+    k_scan<u32><<<tiles, SCAN_THREADS, 0, lc.stream>>>(data, data, n, tileState, &sc->tileCounter, &sc->nnzC);
+    ++*lc.launches;
+}
+
+void launch_scan_map(const LaunchCtx &lc, const u32 *in, u64 *out, u32 n, u64 *tileState, Scalars *sc)
+{
+    if (n == 0) return;
+    const u32 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    cudaMemsetAsync(tileState, 0, (size_t)tiles * sizeof(u64), lc.stream);
+    k_scan<u64><<<tiles, SCAN_THREADS, 0, lc.stream>>>(in, out, n, tileState, &sc->mapTileCounter, &sc->mapTotal);
     ++*lc.launches;
 }
 

@@ -1,39 +1,38 @@
 // speck_b200/csrc/kernels_rank.cu -- launchers of the rank row classes (rank_cta.cuh).
-// Four launch shapes (128 / 256 / 512 / 1024 threads, 8 product slots per thread): `capProducts` is the
-// largest product count among the rows of the launch.
+// Four launch shapes (128 / 256 / 512 / 1024 threads, 8 product slots per thread; 4 and 16 slots per
+// thread were measured slower, profiles/r1_notes.md): `capProducts` is the largest product count among
+// the rows of the launch.
 #include "rank_cta.cuh"
 
 namespace sb {
 
-// product slots per thread: 8 (128..1024 threads) or 4 (256..1024 threads, 8 for the largest shape)
-static int g_rankE = 8;
-void set_rank_slots(int e) { g_rankE = (e == 4 || e == 16) ? e : 8; }
+constexpr int RANK_E = 8;
+
+#define SB_RANK_SHAPES(CALL)                       \
+    do {                                           \
+        if (capProducts <= 128 * RANK_E) CALL(128);      \
+        else if (capProducts <= 256 * RANK_E) CALL(256); \
+        else if (capProducts <= 512 * RANK_E) CALL(512); \
+        else CALL(1024);                           \
+    } while (0)
 
 void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                           const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, const u32 *rowMin,
-                          const u32 *rowMax, u32 *rowNnz)
+                          const u32 *rowMax, u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg,
+                          unsigned short *rankMap)
 {
     if (count == 0) return;
     const float *nv = nullptr;
-#define SB_RANK_SYM(TH, E) \
-    launch_rank_rows<TH, E, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax, rowNnz, nullptr, nullptr)
-    if (g_rankE == 4) {
-        if (capProducts <= 1024) SB_RANK_SYM(256, 4);
-        else if (capProducts <= 2048) SB_RANK_SYM(512, 4);
-        else if (capProducts <= 4096) SB_RANK_SYM(1024, 4);
-        else SB_RANK_SYM(1024, 8);
-    } else if (g_rankE == 16) {
-        if (capProducts <= 1024) SB_RANK_SYM(64, 16);
-        else if (capProducts <= 2048) SB_RANK_SYM(128, 16);
-        else if (capProducts <= 4096) SB_RANK_SYM(256, 16);
-        else SB_RANK_SYM(512, 16);
-    } else {
-        if (capProducts <= 1024) SB_RANK_SYM(128, 8);
-        else if (capProducts <= 2048) SB_RANK_SYM(256, 8);
-        else if (capProducts <= 4096) SB_RANK_SYM(512, 8);
-        else SB_RANK_SYM(1024, 8);
-    }
-#undef SB_RANK_SYM
+#define SB_RANK_CNT(TH)                                                                                              \
+    launch_rank_rows<TH, RANK_E, float, RANK_COUNT>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax, \
+                                                    nullptr, nullptr, nullptr, rowNnz, nullptr, nullptr)
+#define SB_RANK_MAP(TH)                                                                                              \
+    launch_rank_rows<TH, RANK_E, float, RANK_MAP>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax,   \
+                                                  desc, aSeg, rankMap, rowNnz, nullptr, nullptr)
+    if (desc && aSeg && rankMap) SB_RANK_SHAPES(SB_RANK_MAP);
+    else SB_RANK_SHAPES(SB_RANK_CNT);
+#undef SB_RANK_CNT
+#undef SB_RANK_MAP
 }
 
 template <typename T>
@@ -43,31 +42,32 @@ void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, 
 {
     if (count == 0) return;
     u32 *rp = const_cast<u32 *>(cRp);
-#define SB_RANK_NUM(TH, E) \
-    launch_rank_rows<TH, E, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax, rp, cCi, cV)
-    if (g_rankE == 4) {
-        if (capProducts <= 1024) SB_RANK_NUM(256, 4);
-        else if (capProducts <= 2048) SB_RANK_NUM(512, 4);
-        else if (capProducts <= 4096) SB_RANK_NUM(1024, 4);
-        else SB_RANK_NUM(1024, 8);
-    } else if (g_rankE == 16) {
-        if (capProducts <= 1024) SB_RANK_NUM(64, 16);
-        else if (capProducts <= 2048) SB_RANK_NUM(128, 16);
-        else if (capProducts <= 4096) SB_RANK_NUM(256, 16);
-        else SB_RANK_NUM(512, 16);
-    } else {
-        if (capProducts <= 1024) SB_RANK_NUM(128, 8);
-        else if (capProducts <= 2048) SB_RANK_NUM(256, 8);
-        else if (capProducts <= 4096) SB_RANK_NUM(512, 8);
-        else SB_RANK_NUM(1024, 8);
-    }
+#define SB_RANK_NUM(TH)                                                                                               \
+    launch_rank_rows<TH, RANK_E, T, RANK_NUMERIC>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax,   \
+                                                  nullptr, nullptr, nullptr, rp, cCi, cV)
+    SB_RANK_SHAPES(SB_RANK_NUM);
 #undef SB_RANK_NUM
 }
-template void launch_rank_numeric<double>(const LaunchCtx &, u32, const u32 *, u32, const u32 *, const u32 *,
-                                          const double *, const u32 *, const u32 *, const double *, const u32 *,
-                                          const u32 *, const u32 *, const u32 *, u32 *, double *);
-template void launch_rank_numeric<float>(const LaunchCtx &, u32, const u32 *, u32, const u32 *, const u32 *,
-                                         const float *, const u32 *, const u32 *, const float *, const u32 *,
-                                         const u32 *, const u32 *, const u32 *, u32 *, float *);
+
+template <typename T>
+void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
+                            const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi,
+                            T *cV)
+{
+    if (count == 0) return;
+#define SB_MAP_NUM(TH) launch_map_rows_cta<TH, RANK_E, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
+    SB_RANK_SHAPES(SB_MAP_NUM);
+#undef SB_MAP_NUM
+}
+
+#define SB_INST(T)                                                                                                     \
+    template void launch_rank_numeric<T>(const LaunchCtx &, u32, const u32 *, u32, const u32 *, const u32 *, const T *, \
+                                         const u32 *, const u32 *, const T *, const u32 *, const u32 *, const u32 *,   \
+                                         const u32 *, u32 *, T *);                                                     \
+    template void launch_map_numeric_cta<T>(const LaunchCtx &, u32, const RowDesc *, u32, const uint2 *, const T *,    \
+                                            const u32 *, const T *, const unsigned short *, u32 *, T *);
+SB_INST(double)
+SB_INST(float)
+#undef SB_INST
 
 }  // namespace sb

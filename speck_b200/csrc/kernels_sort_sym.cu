@@ -3,13 +3,25 @@
 
 namespace sb {
 
-void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, const u32 *perm, u32 count, const u32 *aRp,
-                          const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, u32 *rowNnz)
+void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
+                          const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps,
+                          u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg, unsigned short *rankMap)
 {
     if (count == 0) return;
     const float *nv = nullptr;
-#define SB_SYM(G, E) \
-    launch_sort_rows<G, E, u32, float, false>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz, nullptr, nullptr)
+    const bool map = desc && aSeg && rankMap && sortClass < NUM_WARP_SORT;
+#define SB_SYM(G, E)                                                                                                      \
+    do {                                                                                                                  \
+        if (!map)                                                                                                         \
+            launch_sort_rows<G, E, u32, float, SORT_COUNT>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz,   \
+                                                           nullptr, nullptr);                                             \
+        else if (wideKeys)                                                                                                \
+            launch_sort_rows<G, E, u64, float, SORT_MAP>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz,     \
+                                                         nullptr, nullptr, desc, aSeg, rankMap);                          \
+        else                                                                                                              \
+            launch_sort_rows<G, E, u32, float, SORT_MAP>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowNnz,     \
+                                                         nullptr, nullptr, desc, aSeg, rankMap);                          \
+    } while (0)
     switch (sortClass) {
         case 0: SB_SYM(4, 1); break;
         case 1: SB_SYM(8, 1); break;

@@ -58,6 +58,34 @@ __device__ __forceinline__ u32 cta_exclusive_scan(u32 v, u32 *sWarp, u32 *total)
     return sWarp[warp] + incl - v;
 }
 
+// Blocked product assignment of the CTA kernels: thread t owns the row's products gp in [t * EP, (t + 1) * EP),
+// EP = ceil(n / THREADS) <= E (gp = index in the row's flat enumeration: A entries ascending, then B-row order).
+// A thread locates the A entry of its first product through the owner table and then walks forward: consecutive
+// products mostly stay inside one B row, so the per-product cost is one compare.  (The strided assignment used
+// before needed a table lookup + walk per product: ~25 of the ~50 gather instructions per product.)
+template <typename T, bool WITH_VALUE>
+struct SegWalk {
+    u32 lo, segEnd, segBs;
+    T av;
+    __device__ __forceinline__ void start(u32 p, const unsigned short *sTab, const u32 *sIncl, const u32 *sBs, const T *sAv)
+    {
+        lo = sTab[p >> 5];
+        while ((segEnd = sIncl[lo]) <= p) ++lo;
+        segBs = sBs[lo];
+        if (WITH_VALUE) av = sAv[lo];
+    }
+    // position in B (col_ids / data index) of product p of the batch, p not below the previous call's
+    __device__ __forceinline__ u32 locate(u32 p, const u32 *sIncl, const u32 *sBs, const T *sAv)
+    {
+        if (p >= segEnd) {
+            do { ++lo; segEnd = sIncl[lo]; } while (p >= segEnd);
+            segBs = sBs[lo];
+            if (WITH_VALUE) av = sAv[lo];
+        }
+        return segBs + p;
+    }
+};
+
 // Shared memory of a CTA of THREADS threads (CAP = THREADS * E product slots), 16-byte aligned pieces, all
 // offsets compile-time:
 //   outVal[CAP] T | sAv[THREADS] T | top[1024] | topPre[1024] u16 | leaf[CAP] | leafPre[CAP] u16 |
@@ -112,13 +140,23 @@ __device__ __forceinline__ u32 rank_scan_level(const u32 *bits, unsigned short *
     return tot;
 }
 
-template <int THREADS, int E, typename T, bool NUMERIC>
+// MODE: RANK_COUNT   symbolic, distinct columns per row only
+//       RANK_NUMERIC self-contained numeric phase (no rank map available)
+//       RANK_MAP     symbolic + rank map: every product's sorted position (and whether it is the first
+//                    product of its column) is recorded, so the numeric phase needs no bitmaps at all
+//                    (k_map_rows_cta below)
+enum { RANK_COUNT = 0, RANK_NUMERIC = 1, RANK_MAP = 2 };
+
+template <int THREADS, int E, typename T, int MODE>
 __global__ void __launch_bounds__(THREADS)
 k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32 *__restrict__ aCi,
             const T *__restrict__ aV, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
             const T *__restrict__ bV, const u32 *__restrict__ rowOps, const u32 *__restrict__ rowMin,
-            const u32 *__restrict__ rowMax, u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV)
+            const u32 *__restrict__ rowMax, const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
+            unsigned short *__restrict__ rankMap, u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV)
 {
+    constexpr bool NUMERIC = MODE == RANK_NUMERIC;
+    constexpr bool DESC = MODE == RANK_MAP;   // row parameters from the descriptor, B-row bounds from aSeg
     using L = RankLayout<THREADS, E, T, NUMERIC>;
     constexpr u32 NONE = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -136,11 +174,21 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     __shared__ u32 sWarp[33];
 
     const u32 tid = threadIdx.x;
-    const u32 row = perm[blockIdx.x];
-    const u32 n = rowOps[row];                               // products of the row, <= CAP
-    const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
-    const u32 cmin = rowMin[row];
-    const u32 topWords = ((rowMax[row] - cmin) >> 10) + 1;   // <= RANK_TOP_WORDS: the host checks cols(B)
+    u32 row, n, aBeg, aEnd, cmin, cmax;
+    u64 mapOff = 0;
+    if (DESC) {
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(desc + blockIdx.x));
+        const uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(desc + blockIdx.x) + 1);
+        aBeg = d0.x; aEnd = d0.x + d0.y; n = d0.z; row = d0.w;
+        cmin = d1.x; cmax = d1.y;
+        mapOff = ((u64)d1.w << 32) | d1.z;
+    } else {
+        row = perm[blockIdx.x];
+        n = rowOps[row];                                     // products of the row, <= CAP
+        aBeg = aRp[row]; aEnd = aRp[row + 1];
+        cmin = rowMin[row]; cmax = rowMax[row];
+    }
+    const u32 topWords = ((cmax - cmin) >> 10) + 1;          // <= RANK_TOP_WORDS: the host checks cols(B)
     u32 cBase = 0, nnzRow = 0;
     if (NUMERIC) {
         cBase = cRp[row];
@@ -151,8 +199,10 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     __syncthreads();
 
     // ---------------------------------------------------------------- gather (flat over the CTA)
-    // product gp (row-wide index: k ascending, then B-row order) lives in thread gp % THREADS, slot gp / THREADS;
-    // slots i with i * THREADS >= n are empty in every thread: all slot loops stop there (CTA-uniform)
+    // product gp (row-wide index: k ascending, then B-row order) lives in thread gp / EP, slot gp % EP (SegWalk);
+    // slots i >= EP are empty in every thread: all slot loops stop there (CTA-uniform)
+    const u32 EP = (n + THREADS - 1) / THREADS;
+    const u32 myFirst = tid * EP;
     u32 col[E];
     T prod[E];
 #pragma unroll
@@ -163,9 +213,15 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         const u32 nb = min((u32)THREADS, aEnd - ab);
         u32 bs = 0, len = 0;
         if (tid < nb) {
-            const u32 k = __ldg(aCi + ab + tid);
-            bs = __ldg(bRp + k);
-            len = __ldg(bRp + k + 1) - bs;
+            if (DESC) {
+                const uint2 seg = __ldg(aSeg + ab + tid);
+                bs = seg.x;
+                len = seg.y - seg.x;
+            } else {
+                const u32 k = __ldg(aCi + ab + tid);
+                bs = __ldg(bRp + k);
+                len = __ldg(bRp + k + 1) - bs;
+            }
             if (NUMERIC) sAv[tid] = __ldg(aV + ab + tid);
         }
         u32 total;
@@ -178,34 +234,31 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         }
         __syncthreads();
         constexpr int GU = E < 4 ? E : 4;   // products per thread in flight
+        const u32 first = max(myFirst, base), last = min(min(myFirst + EP, n), base + total);
+        SegWalk<T, NUMERIC> walk;
+        if (first < last) walk.start(first - base, sTab, sIncl, sBs, sAv);
 #pragma unroll
         for (int i0 = 0; i0 < E; i0 += GU) {
-            if ((u32)i0 * THREADS >= base + total) break;           // CTA-uniform
-            if ((u32)(i0 + GU) * THREADS <= base) continue;         // CTA-uniform (earlier batch)
+            if ((u32)i0 >= EP) break;           // CTA-uniform
             u32 q[GU], cc[GU];
             T av[GU], bv[GU];
 #pragma unroll
             for (int u = 0; u < GU; ++u) {
-                const u32 gp = (u32)(i0 + u) * THREADS + tid;
-                const u32 p = gp - base;
+                const u32 gp = myFirst + (u32)(i0 + u);
                 q[u] = NONE;
                 av[u] = (T)0;
-                if (p < total) {   // gp < base wraps p beyond any total
-                    u32 lo = sTab[p >> 5];
-                    while (sIncl[lo] <= p) ++lo;
-                    q[u] = sBs[lo] + p;
-                    if (NUMERIC) av[u] = sAv[lo];
+                if (gp >= first && gp < last) {
+                    q[u] = walk.locate(gp - base, sIncl, sBs, sAv);
+                    if (NUMERIC) av[u] = walk.av;
                 }
             }
 #pragma unroll
             for (int u = 0; u < GU; ++u) {
-                if ((u32)(i0 + u) * THREADS >= base + total) break;
                 cc[u] = q[u] != NONE ? __ldg(bCi + q[u]) : 0u;
                 bv[u] = (NUMERIC && q[u] != NONE) ? __ldg(bV + q[u]) : (T)0;
             }
 #pragma unroll
             for (int u = 0; u < GU; ++u) {
-                if ((u32)(i0 + u) * THREADS >= base + total) break;
                 if (q[u] != NONE) {
                     const u32 c = cc[u] - cmin;
                     col[i0 + u] = c;
@@ -226,25 +279,38 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     u32 dup = 0;   // bit i: slot i is not the first product of its column
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-        if ((u32)i * THREADS >= n) break;
+        if ((u32)i >= EP) break;
         if (col[i] != NONE) {
             const u32 c = col[i];
             const u32 tw = c >> 10, tb = (c >> 5) & 31;
             const u32 s = topPre[tw] + __popc(top[tw] & ((1u << tb) - 1u));
             const u32 bit = 1u << (c & 31);
             const u32 old = atomicOr(&leaf[s], bit);
-            if (NUMERIC) {
-                if (old & bit) dup |= 1u << i;
-                leafId[s] = (unsigned short)(c >> 5);   // every product of the word stores the same id
-            }
+            if (MODE != RANK_COUNT && (old & bit)) dup |= 1u << i;
+            if (NUMERIC) leafId[s] = (unsigned short)(c >> 5);   // every product of the word stores the same id
             col[i] = (s << 5) | (c & 31u);              // from here on: leaf slot and bit
         }
     }
     __syncthreads();
 
-    if (!NUMERIC) {
+    if (MODE == RANK_COUNT) {
         const u32 distinct = rank_scan_level<THREADS, false>(leaf, nullptr, leaves, sWarp);
         if (tid == 0) cRp[row] = distinct;
+        return;
+    } else if (MODE == RANK_MAP) {
+        const u32 distinct = rank_scan_level<THREADS, true>(leaf, leafPre, leaves, sWarp);
+        if (tid == 0) cRp[row] = distinct;
+        __syncthreads();
+        unsigned short *map = rankMap + mapOff;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if ((u32)i >= EP) break;
+            if (col[i] != NONE) {
+                const u32 s = col[i] >> 5, b = col[i] & 31;
+                const u32 rank = leafPre[s] + __popc(leaf[s] & ((1u << b) - 1u));
+                map[myFirst + (u32)i] = (unsigned short)(rank | (((dup >> i) & 1u) ? MAP_DUP : 0u));
+            }
+        }
         return;
     } else {
         rank_scan_level<THREADS, true>(leaf, leafPre, leaves, sWarp);
@@ -252,7 +318,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         // ------------------------------------------------------------ first product of a column: plain stores
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            if ((u32)i * THREADS >= n) break;
+            if ((u32)i >= EP) break;
             if (col[i] != NONE) {
                 const u32 s = col[i] >> 5, b = col[i] & 31;
                 const u32 rank = leafPre[s] + __popc(leaf[s] & ((1u << b) - 1u));
@@ -278,16 +344,163 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     }
 }
 
-template <int THREADS, int E, typename T, bool NUMERIC>
+template <int THREADS, int E, typename T, int MODE>
 void launch_rank_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                       const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, const u32 *rowMin,
-                      const u32 *rowMax, u32 *cRp, u32 *cCi, T *cV)
+                      const u32 *rowMax, const RowDesc *desc, const uint2 *aSeg, unsigned short *rankMap, u32 *cRp,
+                      u32 *cCi, T *cV)
 {
-    using L = RankLayout<THREADS, E, T, NUMERIC>;
-    auto kern = k_rank_rows<THREADS, E, T, NUMERIC>;
+    using L = RankLayout<THREADS, E, T, MODE == RANK_NUMERIC>;
+    auto kern = k_rank_rows<THREADS, E, T, MODE>;
     if (L::SMEM > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
-    kern<<<count, THREADS, L::SMEM, lc.stream>>>(perm, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax, cRp, cCi, cV);
+    kern<<<count, THREADS, L::SMEM, lc.stream>>>(perm, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax, desc, aSeg,
+                                                 rankMap, cRp, cCi, cV);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Numeric phase of a mapped row (CTA per row): gather, multiply, scatter by the recorded rank into a
+// shared staging row, write the row to C coalesced.  No bitmaps, no scans beyond the B-row lengths.
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int E, typename T>
+struct MapCtaLayout {
+    static constexpr size_t al(size_t b) { return (b + 15) / 16 * 16; }
+    static constexpr size_t CAP = (size_t)THREADS * E;
+    static constexpr size_t OUTVAL = 0;
+    static constexpr size_t SAV = OUTVAL + al(CAP * sizeof(T));
+    static constexpr size_t OUTCOL = SAV + al(THREADS * sizeof(T));
+    static constexpr size_t SINCL = OUTCOL + al(CAP * 4);
+    static constexpr size_t SBS = SINCL + al(THREADS * 4);
+    static constexpr size_t STAB = SBS + al(THREADS * 4);
+    static constexpr size_t SMEM = STAB + al(CAP / 32 * 2);
+};
+
+template <int THREADS, int E, typename T>
+__global__ void __launch_bounds__(THREADS)
+k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg, const T *__restrict__ aV,
+               const u32 *__restrict__ bCi, const T *__restrict__ bV, const unsigned short *__restrict__ rankMap,
+               u32 *__restrict__ cCi, T *__restrict__ cV)
+{
+    using L = MapCtaLayout<THREADS, E, T>;
+    constexpr u32 NONE = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    T *outVal = reinterpret_cast<T *>(smemRaw + L::OUTVAL);
+    T *sAv = reinterpret_cast<T *>(smemRaw + L::SAV);
+    u32 *outCol = reinterpret_cast<u32 *>(smemRaw + L::OUTCOL);
+    u32 *sIncl = reinterpret_cast<u32 *>(smemRaw + L::SINCL);
+    u32 *sBs = reinterpret_cast<u32 *>(smemRaw + L::SBS);
+    unsigned short *sTab = reinterpret_cast<unsigned short *>(smemRaw + L::STAB);
+    __shared__ u32 sWarp[33];
+
+    const u32 tid = threadIdx.x;
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(desc + blockIdx.x));
+    const uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(desc + blockIdx.x) + 1);
+    const u32 aBeg = d0.x, aEnd = d0.x + d0.y, n = d0.z;
+    const u32 cBase = d1.x, nnzRow = d1.y;
+    const unsigned short *map = rankMap + (((u64)d1.w << 32) | d1.z);
+    const u32 EP = (n + THREADS - 1) / THREADS;   // products per thread, blocked assignment (SegWalk)
+    const u32 myFirst = tid * EP;
+
+    // Products that are not the first of their column are added once every first product is in place: their
+    // slots are remembered in a bit mask and re-located from the (still valid) tables after a barrier.  Rows
+    // whose A entries need several batches (rare) add every product into a zeroed staging row instead.
+    const bool multi = (aEnd - aBeg) > (u32)THREADS;
+    if (multi)
+        for (u32 j = tid; j < nnzRow; j += THREADS) outVal[j] = (T)0;
+    u32 dup = 0;
+    u32 base = 0;
+#pragma unroll 1
+    for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
+        const u32 nb = min((u32)THREADS, aEnd - ab);
+        u32 bs = 0, len = 0;
+        if (tid < nb) {
+            const uint2 seg = __ldg(aSeg + ab + tid);
+            bs = seg.x;
+            len = seg.y - seg.x;
+            sAv[tid] = __ldg(aV + ab + tid);
+        }
+        u32 total;
+        const u32 excl = cta_exclusive_scan<THREADS>(len, sWarp, &total);
+        sIncl[tid] = excl + len;
+        sBs[tid] = bs - excl;  // q = sBs[owner] + p
+        if (len) {             // owner table: sTab[b] = entry owning product 32*b of this batch
+            const u32 bLast = (excl + len - 1) >> 5;
+            for (u32 b = (excl + 31) >> 5; b <= bLast; ++b) sTab[b] = (unsigned short)tid;
+        }
+        __syncthreads();
+        constexpr int GU = E < 4 ? E : 4;   // products per thread in flight
+        const u32 first = max(myFirst, base), last = min(min(myFirst + EP, n), base + total);
+        SegWalk<T, true> walk;
+        if (first < last) walk.start(first - base, sTab, sIncl, sBs, sAv);
+#pragma unroll
+        for (int i0 = 0; i0 < E; i0 += GU) {
+            if ((u32)i0 >= EP) break;           // CTA-uniform
+            u32 q[GU], cc[GU], code[GU];
+            T av[GU], bv[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const u32 gp = myFirst + (u32)(i0 + u);
+                q[u] = NONE;
+                av[u] = (T)0;
+                code[u] = 0;
+                if (gp >= first && gp < last) {
+                    code[u] = map[gp];
+                    q[u] = walk.locate(gp - base, sIncl, sBs, sAv);
+                    av[u] = walk.av;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                cc[u] = q[u] != NONE ? __ldg(bCi + q[u]) : 0u;
+                bv[u] = q[u] != NONE ? __ldg(bV + q[u]) : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                if (q[u] != NONE) {
+                    const u32 r = code[u] & MAP_RANK_MASK;
+                    const T pr = av[u] * bv[u];
+                    if (multi) {
+                        if (!(code[u] & MAP_DUP)) outCol[r] = cc[u];
+                        atomicAdd(&outVal[r], pr);
+                    } else if (code[u] & MAP_DUP) {
+                        dup |= 1u << (i0 + u);
+                    } else {
+                        outVal[r] = pr;
+                        outCol[r] = cc[u];
+                    }
+                }
+            }
+        }
+        base += total;
+        __syncthreads();
+    }
+    if (__syncthreads_or(dup != 0)) {   // single batch: its tables are still in place
+        while (dup) {
+            const u32 gp = myFirst + (u32)(__ffs(dup) - 1);
+            dup &= dup - 1;
+            SegWalk<T, true> walk;
+            walk.start(gp, sTab, sIncl, sBs, sAv);
+            atomicAdd(&outVal[map[gp] & MAP_RANK_MASK], walk.av * __ldg(bV + walk.segBs + gp));
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (u32 j = tid; j < nnzRow; j += THREADS) {
+        cCi[cBase + j] = outCol[j];
+        cV[cBase + j] = outVal[j];
+    }
+}
+
+template <int THREADS, int E, typename T>
+void launch_map_rows_cta(const LaunchCtx &lc, const RowDesc *desc, u32 count, const uint2 *aSeg, const T *aV,
+                         const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi, T *cV)
+{
+    using L = MapCtaLayout<THREADS, E, T>;
+    auto kern = k_map_rows_cta<THREADS, E, T>;
+    if (L::SMEM > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+    kern<<<count, THREADS, L::SMEM, lc.stream>>>(desc, aSeg, aV, bCi, bV, rankMap, cCi, cV);
     ++*lc.launches;
 }
 

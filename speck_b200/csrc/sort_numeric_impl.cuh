@@ -15,9 +15,9 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
 #define SB_NUM(G, E)                                                                                         \
     do {                                                                                                     \
         if (wideKeys)                                                                                        \
-            launch_sort_rows<G, E, u64, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+            launch_sort_rows<G, E, u64, T, SORT_NUMERIC>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
         else                                                                                                 \
-            launch_sort_rows<G, E, u32, T, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
+            launch_sort_rows<G, E, u32, T, SORT_NUMERIC>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rp, cCi, cV); \
     } while (0)
 #define SB_NUM_CTA(WMAX)                                                                                     \
     do {                                                                                                     \
@@ -46,6 +46,25 @@ void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, cons
     }
 #undef SB_NUM
 #undef SB_NUM_CTA
+}
+
+template <typename T>
+void launch_map_numeric(const LaunchCtx &lc, int sortClass, const RowDesc *desc, u32 count, const uint2 *aSeg,
+                        const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi, T *cV)
+{
+    if (count == 0) return;
+#define SB_MAP(G, N) launch_map_rows<G, N, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
+    switch (sortClass) {
+        case 0: SB_MAP(4, 4); break;
+        case 1: SB_MAP(8, 8); break;
+        case 2: SB_MAP(16, 16); break;
+        case 3: SB_MAP(32, 32); break;
+        case 4: SB_MAP(32, 64); break;
+        case 5: SB_MAP(32, 128); break;
+        case 6: SB_MAP(32, 256); break;
+        default: SB_MAP(32, 512); break;
+    }
+#undef SB_MAP
 }
 
 }  // namespace sb

@@ -95,25 +95,37 @@ __device__ __forceinline__ void bitonic_sort_regs(KeyT (&reg)[E], const u32 l, c
     }
 }
 
-template <int G, int E, typename KeyT, typename T, bool NUMERIC>
+// MODE: SORT_COUNT   symbolic, distinct columns only (keys = columns)
+//       SORT_NUMERIC self-contained numeric phase (keys = col << IDXBITS | product index, values staged)
+//       SORT_MAP     symbolic + rank map: sorted position of every product and its first-of-column flag
+//                    are written to the rank map (common.cuh); the numeric phase is then k_map_rows
+enum { SORT_COUNT = 0, SORT_NUMERIC = 1, SORT_MAP = 2 };
+
+template <int G, int E, typename KeyT, typename T, int MODE>
 struct SortLayout {
     static constexpr int N = G * E;
     static constexpr int NPAD = N + N / 32;            // one pad word per 32: conflict-free blocked write-back
     static constexpr int GROUPS = SORT_BLOCK / G;      // groups (rows) per block
     static constexpr size_t KEY_BYTES = (size_t)GROUPS * NPAD * sizeof(KeyT);
-    static constexpr size_t VAL_BYTES = NUMERIC ? (size_t)GROUPS * N * sizeof(T) : 0;
+    // second array per group: staged values (numeric) or the row's rank codes in product order (map)
+    static constexpr size_t VAL_BYTES = MODE == SORT_NUMERIC ? (size_t)GROUPS * N * sizeof(T)
+                                        : (MODE == SORT_MAP ? (size_t)GROUPS * N * sizeof(unsigned short) : 0);
     static constexpr size_t SMEM = ((KEY_BYTES + 15) / 16) * 16 + VAL_BYTES;
 };
 
-template <int G, int E, typename KeyT, typename T, bool NUMERIC>
+template <int G, int E, typename KeyT, typename T, int MODE>
 __global__ void __launch_bounds__(SORT_BLOCK)
 k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
             const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
             const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
             u32 *cRp /* symbolic: counts out; numeric: offsets in */, u32 *__restrict__ cCi,
-            T *__restrict__ cV)
+            T *__restrict__ cV, const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
+            unsigned short *__restrict__ rankMap)
 {
-    using L = SortLayout<G, E, KeyT, T, NUMERIC>;
+    constexpr bool NUMERIC = MODE == SORT_NUMERIC;
+    constexpr bool DESC = MODE == SORT_MAP;        // row parameters from the descriptor, B-row bounds from aSeg
+    constexpr bool IDXKEYS = MODE != SORT_COUNT;   // keys carry the product index
+    using L = SortLayout<G, E, KeyT, T, MODE>;
     constexpr int N = L::N;
     constexpr int IDXBITS = Log2<N>::value;
     constexpr KeyT SENT = ~(KeyT)0;
@@ -125,15 +137,24 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
     const u32 gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (laneW - l));
     KeyT *keys = reinterpret_cast<KeyT *>(smemRaw) + (size_t)grp * L::NPAD;
     T *vals = reinterpret_cast<T *>(smemRaw + ((L::KEY_BYTES + 15) / 16) * 16) + (size_t)grp * N;
+    unsigned short *codes = reinterpret_cast<unsigned short *>(smemRaw + ((L::KEY_BYTES + 15) / 16) * 16) + (size_t)grp * N;
 
     const u32 gidx = blockIdx.x * L::GROUPS + grp;
     const bool active = gidx < count;
     u32 row = 0, ops = 0, aBeg = 0, aEnd = 0;
+    u64 mapOff = 0;
     if (active) {
-        row = perm[gidx];
-        ops = rowOps[row];
-        aBeg = aRp[row];
-        aEnd = aRp[row + 1];
+        if (DESC) {
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(desc + gidx));
+            const uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(desc + gidx) + 1);
+            aBeg = d0.x; aEnd = d0.x + d0.y; ops = d0.z; row = d0.w;
+            mapOff = ((u64)d1.w << 32) | d1.z;
+        } else {
+            row = perm[gidx];
+            ops = rowOps[row];
+            aBeg = aRp[row];
+            aEnd = aRp[row + 1];
+        }
     }
 
     // ---------------------------------------------------------------- gather
@@ -143,9 +164,15 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
         u32 bs = 0, len = 0;
         T av = (T)0;
         if (ai < aEnd) {
-            const u32 k = __ldg(aCi + ai);
-            bs = __ldg(bRp + k);
-            len = __ldg(bRp + k + 1) - bs;
+            if (DESC) {
+                const uint2 seg = __ldg(aSeg + ai);
+                bs = seg.x;
+                len = seg.y - seg.x;
+            } else {
+                const u32 k = __ldg(aCi + ai);
+                bs = __ldg(bRp + k);
+                len = __ldg(bRp + k + 1) - bs;
+            }
             if (NUMERIC) av = __ldg(aV + ai);
         }
         u32 incl = len;
@@ -172,9 +199,9 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
                 const u32 q = oBs + (p - (oIncl - oLen));
                 const u32 col = __ldg(bCi + q);
                 const u32 gp = base + p;
-                if (NUMERIC) {
+                if (IDXKEYS) {
                     keys[gp] = ((KeyT)col << IDXBITS) | (KeyT)gp;
-                    vals[gp] = oAv * __ldg(bV + q);
+                    if (NUMERIC) vals[gp] = oAv * __ldg(bV + q);
                 } else {
                     keys[gp] = (KeyT)col;
                 }
@@ -194,7 +221,7 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
     __syncwarp(gmask);
     bitonic_sort_regs<G, E, KeyT>(reg, l, gmask);
 
-    if (!NUMERIC) {
+    if (MODE == SORT_COUNT) {
         // ------------------------------------------------------------ symbolic: distinct columns
         KeyT prevLast = __shfl_up_sync(gmask, reg[E - 1], 1, G);
         u32 cnt = 0;
@@ -208,6 +235,40 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
 #pragma unroll
         for (int d = G / 2; d >= 1; d >>= 1) cnt += __shfl_xor_sync(gmask, cnt, d, G);
         if (active && l == 0) cRp[row] = cnt;
+        return;
+    } else if (MODE == SORT_MAP) {
+        // ------------------------------------------------------------ symbolic + rank map
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const u32 idx = l * E + r;
+            keys[idx + (idx >> 5)] = reg[r];
+        }
+        __syncwarp(gmask);
+        constexpr KeyT IDXMASK = ((KeyT)1 << IDXBITS) - 1;
+        u32 running = 0;   // distinct columns before this batch of G sorted products
+        for (u32 i0 = 0; i0 < ops; i0 += G) {
+            const u32 i = i0 + l;
+            const bool valid = i < ops;
+            KeyT key = 0;
+            bool head = false;
+            if (valid) {
+                key = keys[i + (i >> 5)];
+                head = (i == 0) || ((u32)(keys[(i - 1) + ((i - 1) >> 5)] >> IDXBITS) != (u32)(key >> IDXBITS));
+            }
+            const u32 bal = __ballot_sync(gmask, head);
+            const u32 gb = (G == 32) ? bal : ((bal >> (laneW - l)) & ((1u << (G & 31)) - 1u));
+            if (valid) {   // position = heads at or before this product - 1
+                const u32 rank = running + __popc(gb & ((2u << l) - 1u)) - 1u;
+                codes[(u32)(key & IDXMASK)] = (unsigned short)(rank | (head ? 0u : MAP_DUP));
+            }
+            running += __popc(gb);
+        }
+        __syncwarp(gmask);
+        if (active) {
+            unsigned short *map = rankMap + mapOff;
+            for (u32 j = l; j < ops; j += G) map[j] = codes[j];
+            if (l == 0) cRp[row] = running;
+        }
         return;
     } else {
         // ------------------------------------------------------------ numeric: fold runs, write C
@@ -254,17 +315,133 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
     }
 }
 
-template <int G, int E, typename KeyT, typename T, bool NUMERIC>
+template <int G, int E, typename KeyT, typename T, int MODE>
 void launch_sort_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                       const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, u32 *cRp,
-                      u32 *cCi, T *cV)
+                      u32 *cCi, T *cV, const RowDesc *desc = nullptr, const uint2 *aSeg = nullptr,
+                      unsigned short *rankMap = nullptr)
 {
-    using L = SortLayout<G, E, KeyT, T, NUMERIC>;
-    auto kern = k_sort_rows<G, E, KeyT, T, NUMERIC>;
+    using L = SortLayout<G, E, KeyT, T, MODE>;
+    auto kern = k_sort_rows<G, E, KeyT, T, MODE>;
     if (L::SMEM > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
     const u32 grid = (count + L::GROUPS - 1) / L::GROUPS;
-    kern<<<grid, SORT_BLOCK, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV);
+    kern<<<grid, SORT_BLOCK, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV, desc, aSeg,
+                                                   rankMap);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Numeric phase of mapped rows, lane-group classes: one group of G lanes per row of <= N products.
+// Gather as above; every product is scattered to its recorded rank in a shared staging row (plain
+// stores when the row has no repeated column, otherwise shared-memory atomicAdd into a zeroed row),
+// then the row is written to C coalesced.  No sort.
+// ------------------------------------------------------------------------------------------------
+template <int G, int N, typename T>
+struct MapLayout {
+    static constexpr int GROUPS = SORT_BLOCK / G;
+    static constexpr size_t VAL_BYTES = (size_t)GROUPS * N * sizeof(T);
+    static constexpr size_t SMEM = VAL_BYTES + (size_t)GROUPS * N * sizeof(u32);
+};
+
+template <int G, int N, typename T>
+__global__ void __launch_bounds__(SORT_BLOCK)
+k_map_rows(const RowDesc *__restrict__ desc, const u32 count, const uint2 *__restrict__ aSeg,
+           const T *__restrict__ aV, const u32 *__restrict__ bCi, const T *__restrict__ bV,
+           const unsigned short *__restrict__ rankMap, u32 *__restrict__ cCi, T *__restrict__ cV)
+{
+    using L = MapLayout<G, N, T>;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const u32 laneW = threadIdx.x & 31;
+    const u32 l = threadIdx.x % G;
+    const u32 grp = threadIdx.x / G;
+    const u32 gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (laneW - l));
+    T *outVal = reinterpret_cast<T *>(smemRaw) + (size_t)grp * N;
+    u32 *outCol = reinterpret_cast<u32 *>(smemRaw + L::VAL_BYTES) + (size_t)grp * N;
+
+    const u32 gidx = blockIdx.x * L::GROUPS + grp;
+    const bool active = gidx < count;
+    u32 aBeg = 0, aEnd = 0, cBase = 0, nnzRow = 0;
+    bool folds = false;   // some column receives more than one product
+    const unsigned short *map = rankMap;
+    if (active) {
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(desc + gidx));
+        const uint4 d1 = __ldg(reinterpret_cast<const uint4 *>(desc + gidx) + 1);
+        aBeg = d0.x;
+        aEnd = d0.x + d0.y;
+        cBase = d1.x;
+        nnzRow = d1.y;
+        folds = nnzRow < d0.z;
+        map = rankMap + (((u64)d1.w << 32) | d1.z);
+    }
+    if (folds) {
+        for (u32 j = l; j < nnzRow; j += G) outVal[j] = (T)0;
+        __syncwarp(gmask);
+    }
+    u32 base = 0;
+    for (u32 ab = aBeg; ab < aEnd; ab += G) {
+        const u32 ai = ab + l;
+        u32 bs = 0, len = 0;
+        T av = (T)0;
+        if (ai < aEnd) {
+            const uint2 seg = __ldg(aSeg + ai);
+            bs = seg.x;
+            len = seg.y - seg.x;
+            av = __ldg(aV + ai);
+        }
+        u32 incl = len;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const u32 t = __shfl_up_sync(gmask, incl, d, G);
+            if ((int)l >= d) incl += t;
+        }
+        const u32 total = __shfl_sync(gmask, incl, G - 1, G);
+        for (u32 p0 = 0; p0 < total; p0 += G) {
+            const u32 p = p0 + l;
+            u32 lo = 0;
+#pragma unroll
+            for (int s = G / 2; s >= 1; s >>= 1) {
+                const u32 v = __shfl_sync(gmask, incl, lo + s - 1, G);
+                if (v <= p) lo += s;
+            }
+            const u32 oIncl = __shfl_sync(gmask, incl, lo, G);
+            const u32 oLen = __shfl_sync(gmask, len, lo, G);
+            const u32 oBs = __shfl_sync(gmask, bs, lo, G);
+            const T oAv = __shfl_sync(gmask, av, lo, G);
+            if (p < total) {
+                const u32 q = oBs + (p - (oIncl - oLen));
+                const u32 code = map[base + p];
+                const u32 col = __ldg(bCi + q);
+                const T pr = oAv * __ldg(bV + q);
+                const u32 r = code & MAP_RANK_MASK;
+                if (!folds) {
+                    outVal[r] = pr;
+                    outCol[r] = col;
+                } else {
+                    if (!(code & MAP_DUP)) outCol[r] = col;
+                    atomicAdd(&outVal[r], pr);
+                }
+            }
+        }
+        base += total;
+    }
+    __syncwarp(gmask);
+    for (u32 j = l; j < nnzRow; j += G) {
+        cCi[cBase + j] = outCol[j];
+        cV[cBase + j] = outVal[j];
+    }
+}
+
+template <int G, int N, typename T>
+void launch_map_rows(const LaunchCtx &lc, const RowDesc *desc, u32 count, const uint2 *aSeg, const T *aV,
+                     const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi, T *cV)
+{
+    using L = MapLayout<G, N, T>;
+    auto kern = k_map_rows<G, N, T>;
+    if (L::SMEM > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+    const u32 grid = (count + L::GROUPS - 1) / L::GROUPS;
+    kern<<<grid, SORT_BLOCK, L::SMEM, lc.stream>>>(desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV);
     ++*lc.launches;
 }
 

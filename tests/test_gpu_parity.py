@@ -26,15 +26,19 @@ def test_uniform_random(ctx, n, d, seed):
     check_case(ctx, M.uniform_random(n, n, d, seed), what=f"uniform {n} {d}")
 
 
-@pytest.fixture(params=[(8192, 1), (8192, 0), (1024, 1), (64, 1)], ids=["8192-rank", "8192-sort", "1024", "64"])
+@pytest.fixture(params=[(8192, 1, 1), (8192, 1, 0), (8192, 0, 1), (8192, 0, 0), (1024, 1, 1), (64, 1, 1), (64, 1, 0)],
+                ids=["8192-rank-map", "8192-rank", "8192-sort-map", "8192-sort", "1024-map", "64-map", "64"])
 def sort_max(ctx, request):
-    """Run a case with the sort/bitmap switch at several places, and with the rank classes on and
-    off, so that every row class (lane-group sort, rank, CTA sort, bitmap) sees the same inputs."""
+    """Run a case with the sort/bitmap switch at several places, with the rank classes on and off and with
+    and without the symbolic->numeric rank map, so that every kernel family (lane-group sort, rank, CTA
+    sort, bitmap, mapped numeric) sees the same inputs."""
     ctx.set_option("sort_max", request.param[0])
     ctx.set_option("rank_path", request.param[1])
+    ctx.set_option("rank_map", request.param[2])
     yield request.param[0]
     ctx.set_option("sort_max", 8192)
     ctx.set_option("rank_path", 1)
+    ctx.set_option("rank_map", 1)
 
 
 @pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16), (15, 16)])
@@ -80,15 +84,20 @@ def _rows_with_products(targets, cols=4096, seed=0):
     return A, B
 
 
-def test_class_boundaries(ctx):
+@pytest.mark.parametrize("rank_map", [1, 0])
+def test_class_boundaries(ctx, rank_map):
     """product counts straddling every class boundary (4<<c) and the sort/dense switch."""
+    ctx.set_option("rank_map", rank_map)
     targets = []
     for c in range(0, 12):
         b = 4 << c
         targets += [b - 1, b, b + 1]
     targets += [1, 2, 3, 8255, 8256]
     A, B = _rows_with_products(targets, cols=1 << 18)
-    got, st = check_case(ctx, A, B, what="class boundaries")
+    try:
+        got, st = check_case(ctx, A, B, what="class boundaries")
+    finally:
+        ctx.set_option("rank_map", 1)
     assert ndense(st) >= 3
     # CTA classes step by 512 products (2..16 warps): b-1 and b fall in sort{b}, b+1 in sort{b+512}
     for name in ("sort1024", "sort1536", "sort2048", "sort2560", "sort4096", "sort4608", "sort8192"):
