@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libspeck_b200.so")
 
 NUM_CLASSES = 32
 BIN_NAMES = (["direct"] + [f"sort{4 << c}" for c in range(8)] + [f"sort{512 * w}" for w in range(2, 17)]
-             + ["dense_local", "dense"])
+             + ["sort16384", "dense_local", "dense"])
 
 
 class SpeckError(RuntimeError):

@@ -64,8 +64,12 @@ struct speck_ctx {
     void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
     size_t hostOutCap[3] = {};
     speck_csr hostC = {};     // device C kept across *_host calls (reuse rules)
-    u32 sortMax = SORT_MAX_PRODUCTS;
+    u32 sortMax = RANK_MAX_PRODUCTS;  // rows with more products take the bitmap path (clamped per multiply)
     bool rankPath = true;     // rows of 513..8192 products: rank classes instead of the CTA sort classes
+    int symStreams = NSIDE;   // side streams used by the symbolic phase (instruction-bound kernels overlap well)
+    int numStreams = 1;       // ... and by the numeric phase besides the bitmap kernel's own stream: the mapped
+                              // numeric kernels are memory-latency bound and run faster one after the other
+    int mapCtaMin = 6;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
     bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
     u32 launches = 0;
     speck_stats stats = {};
@@ -148,6 +152,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // wider matrices send those rows to the bitmap path instead of sorting u64 keys.
     u32 sortMax = c->sortMax;
     const bool useRank = c->rankPath && colsB <= RANK_EXTENT_LIMIT;  // rank classes have no key-width limit
+    const bool wantMap = c->rankMapOn;
+    if (!(useRank && wantMap) && sortMax > SORT_MAX_PRODUCTS) sortMax = SORT_MAX_PRODUCTS;  // 8193..16384: mapped rank kernels only
     if (sortMax > 1024 && !useRank) {  // largest power-of-two network whose keys fit 32 bits: cols * N <= 2^32
         u32 fit = 8192;
         while (fit > 1024 && ((u64)colsB * fit) > (1ull << 32)) fit >>= 1;
@@ -162,7 +168,6 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     if ((rc = ensure(c->rowMin, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->rowMax, (size_t)rows * 4))) return rc;
     if ((rc = ensure(c->tileState, scan_tile_state_bytes(rows + 1)))) return rc;
-    const bool wantMap = c->rankMapOn;
     if (wantMap) {
         if ((rc = ensure(c->mapLen, (size_t)(rows + 1) * 4))) return rc;
         if ((rc = ensure(c->mapBase, (size_t)(rows + 1) * 8))) return rc;
@@ -206,7 +211,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
 
     // first bin of each rank launch group: CTA class c holds rows of <= 512 * (c + 2) products
     const int cta0 = BIN_SORT0 + NUM_WARP_SORT;
-    const int rankGroupFirst[5] = {cta0, cta0 + 1, cta0 + 3, cta0 + 7, cta0 + NUM_CTA_SORT};
+    const int rankGroupFirst[6] = {cta0, cta0 + 1, cta0 + 3, cta0 + 7, cta0 + 15, cta0 + NUM_CTA_SORT};
+    constexpr int RANK_GROUPS = 5;   // products <= 1024 << g
 
     // bitmaps of the local-dense rows are kept from the symbolic to the numeric phase (2 KB per row)
     u32 *bitmapStore = nullptr;
@@ -241,17 +247,22 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     for (int loc = 0; loc < 2; ++loc) {
         const int bin = loc ? BIN_DENSE_LOCAL : BIN_DENSE;
         if (!s1.binCount[bin]) continue;
-        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         launch_dense_symbolic(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[loc], aRp,
                               aCi, bRp, bCi, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp);
     }
     // rank classes: the CTA sort bins grouped by launch shape (products <= 8192 / 4096 / 2048 / 1024)
     if (useRank) {
-        for (int g = 3; g >= 0; --g) {
+        for (int g = RANK_GROUPS - 1; g >= 0; --g) {
             const int b0 = rankGroupFirst[g], b1 = rankGroupFirst[g + 1];
             const u32 cnt = binStart[b1] - binStart[b0];
             if (!cnt) continue;
-            LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+            LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
+            if (g == RANK_GROUPS - 1 && !rankMap) {  // no rank map could be allocated: the bitmap kernel takes these rows
+                launch_dense_symbolic(ls, false, perm + binStart[b0], cnt, &c->dSc->denseCounter[4], aRp, aCi, bRp, bCi, colsB,
+                                      rowMin, rowMax, nullptr, cRp);
+                continue;
+            }
             launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp,
                                  desc ? desc + binStart[b0] : nullptr, aSeg, rankMap);
         }
@@ -259,7 +270,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
-        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
                              rowOps, cRp, desc ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
     }
@@ -303,16 +314,21 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     for (int loc = 0; loc < 2; ++loc) {
         const int bin = loc ? BIN_DENSE_LOCAL : BIN_DENSE;
         if (!s1.binCount[bin]) continue;
-        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        LaunchCtx ls{c->side[NSIDE - 1], c->smCount, &c->launches};
         launch_dense_numeric<T>(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[2 + loc],
                                 aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV);
     }
     if (useRank) {
-        for (int g = 3; g >= 0; --g) {
+        for (int g = RANK_GROUPS - 1; g >= 0; --g) {
             const int b0 = rankGroupFirst[g], b1 = rankGroupFirst[g + 1];
             const u32 cnt = binStart[b1] - binStart[b0];
             if (!cnt) continue;
-            LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+            LaunchCtx ls{c->side[sidx++ % c->numStreams], c->smCount, &c->launches};
+            if (g == RANK_GROUPS - 1 && !rankMap) {
+                launch_dense_numeric<T>(ls, false, perm + binStart[b0], cnt, &c->dSc->denseCounter[5], aRp, aCi, aV, bRp, bCi,
+                                        bV, colsB, rowMin, rowMax, nullptr, cRp, cCi, cV);
+                continue;
+            }
             if (rankMap)
                 launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
             else
@@ -323,15 +339,17 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
-        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
-        if (rankMap && sc < NUM_WARP_SORT)
+        LaunchCtx ls{c->side[sidx++ % c->numStreams], c->smCount, &c->launches};
+        if (rankMap && sc < NUM_WARP_SORT && sc >= c->mapCtaMin)   // rows of <= 4 << sc products: 32 / 64 threads x 8 slots
+            launch_map_numeric_cta<T>(ls, 4u << sc, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
+        else if (rankMap && sc < NUM_WARP_SORT)
             launch_map_numeric<T>(ls, sc, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
         else
             launch_sort_numeric<T>(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV,
                                    bRp, bCi, bV, rowOps, cRp, cCi, cV);
     }
     {
-        LaunchCtx ls{c->side[sidx++ % NSIDE], c->smCount, &c->launches};
+        LaunchCtx ls{c->side[sidx++ % c->numStreams], c->smCount, &c->launches};
         launch_direct_numeric<T>(ls, perm + binStart[BIN_DIRECT], s1.binCount[BIN_DIRECT], aRp, aCi, aV, bRp, bCi, bV,
                                  cRp, cCi, cV);
     }
@@ -643,9 +661,20 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
 {
     if (!c || !key) return fail(SPECK_ERR_INVALID, "null argument");
     if (!strcmp(key, "sort_max")) {
-        if (value < 4 || value > (long long)SORT_MAX_PRODUCTS || ((value & (value - 1)) && value % 512))
-            return fail(SPECK_ERR_INVALID, "sort_max must be a power of two or a multiple of 512 in [4, %u]", SORT_MAX_PRODUCTS);
+        if (value < 4 || value > (long long)RANK_MAX_PRODUCTS || ((value & (value - 1)) && (value % 512 || value > SORT_MAX_PRODUCTS)))
+            return fail(SPECK_ERR_INVALID, "sort_max must be a power of two or a multiple of 512 (up to %u) in [4, %u]",
+                        SORT_MAX_PRODUCTS, RANK_MAX_PRODUCTS);
         c->sortMax = (u32)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "sym_streams") || !strcmp(key, "num_streams")) {
+        if (value < 1 || value > NSIDE) return fail(SPECK_ERR_INVALID, "%s must be in [1, %d]", key, NSIDE);
+        (key[0] == 's' ? c->symStreams : c->numStreams) = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "map_cta_min")) {
+        if (value < 4 || value > NUM_WARP_SORT) return fail(SPECK_ERR_INVALID, "map_cta_min must be in [4, %d]", NUM_WARP_SORT);
+        c->mapCtaMin = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "rank_map")) {

@@ -24,7 +24,7 @@ typedef uint64_t u64;
 namespace sb {
 
 constexpr int NUM_WARP_SORT = 8;            // lane-group classes: 4, 8, ..., 512 products
-constexpr int NUM_CTA_SORT = 15;            // CTA classes: 2..16 warps x 512 keys = 1024, 1536, ..., 8192 products
+constexpr int NUM_CTA_SORT = 16;            // CTA classes: 1024, 1536, ..., 8192 products (steps of 512) and 16384
 constexpr int NUM_SORT = NUM_WARP_SORT + NUM_CTA_SORT;
 constexpr int BIN_DIRECT = 0;
 constexpr int BIN_SORT0 = 1;
@@ -33,7 +33,8 @@ constexpr int BIN_DENSE = BIN_DENSE_LOCAL + 1;          // 25: bitmap path, wide
 constexpr int NUM_BINS = BIN_DENSE + 1;                 // 26
 constexpr int DENSE_LOCAL_BITS = 14;
 constexpr u32 DENSE_LOCAL_COLS = (1u << DENSE_LOCAL_BITS) - 128u;  // window starts chunk-aligned below the row minimum
-constexpr u32 SORT_MAX_PRODUCTS = 8192;
+constexpr u32 SORT_MAX_PRODUCTS = 8192;     // largest row of the CTA sort kernels (sort_cta.cuh)
+constexpr u32 RANK_MAX_PRODUCTS = 16384;    // largest row of the rank kernels (rank_cta.cuh): 1024 threads x 16 slots
 
 // Device-resident scalars of one multiply; mirrored into pinned host memory.
 struct Scalars {
@@ -42,7 +43,8 @@ struct Scalars {
     u32 maxRowProducts;
     u32 binCount[NUM_BINS];   // rows per bin (written by k_analyze)
     u32 binCursor[NUM_BINS];  // scatter cursors (k_bin_scatter)
-    u32 denseCounter[4];      // dynamic row queues of the dense kernels (symbolic/numeric x local/wide)
+    u32 denseCounter[6];      // dynamic row queues of the dense kernels (symbolic/numeric x local/wide, + the
+                              // largest rank bin when no rank map could be allocated)
     u32 tileCounter;          // dynamic tile ids of the row_ptr scan
     u32 mapTileCounter;       // dynamic tile ids of the rank-map offset scan
     u64 mapTotal;             // entries of the rank map (products of all mapped rows)
@@ -74,6 +76,7 @@ __host__ __device__ __forceinline__ int classify_row(u32 ops, u32 aLen, u32 exte
     if (aLen == 1) return BIN_DIRECT;
     const bool banded = ops >= 128u && extent <= 4u * ops;
     if (ops > sortMax || banded) return extent <= DENSE_LOCAL_COLS ? BIN_DENSE_LOCAL : BIN_DENSE;
+    if (ops > SORT_MAX_PRODUCTS) return BIN_SORT0 + NUM_SORT - 1;                       // 8193..16384 (rank kernels only)
     if (ops > 512u) return BIN_SORT0 + NUM_WARP_SORT + (int)((ops + 511u) / 512u) - 2;  // 2..16 warps
     int c = 0;
     while ((4u << c) < ops) ++c;

@@ -1,19 +1,25 @@
 // speck_b200/csrc/kernels_rank.cu -- launchers of the rank row classes (rank_cta.cuh).
-// Four launch shapes (128 / 256 / 512 / 1024 threads, 8 product slots per thread; 4 and 16 slots per
-// thread were measured slower, profiles/r1_notes.md): `capProducts` is the largest product count among
-// the rows of the launch.
+// Launch shapes: 128 / 256 / 512 / 1024 threads with 8 product slots per thread (4 and 16 slots per thread
+// were measured slower on the same rows, profiles/r1_notes.md), and 1024 x 16 for rows of 8193..16384
+// products.  `capProducts` is the largest product count among the rows of the launch.
 #include "rank_cta.cuh"
 
 namespace sb {
 
 constexpr int RANK_E = 8;
 
-#define SB_RANK_SHAPES(CALL)                       \
-    do {                                           \
-        if (capProducts <= 128 * RANK_E) CALL(128);      \
-        else if (capProducts <= 256 * RANK_E) CALL(256); \
-        else if (capProducts <= 512 * RANK_E) CALL(512); \
-        else CALL(1024);                           \
+#define SB_RANK_SHAPES8(CALL)                               \
+    do {                                                    \
+        if (capProducts <= 128 * RANK_E) CALL(128, RANK_E);       \
+        else if (capProducts <= 256 * RANK_E) CALL(256, RANK_E);  \
+        else if (capProducts <= 512 * RANK_E) CALL(512, RANK_E);  \
+        else CALL(1024, RANK_E);                            \
+    } while (0)
+// ... plus the 16384-product shape, which exists for the mapped kernels only
+#define SB_RANK_SHAPES(CALL)                                        \
+    do {                                                            \
+        if (capProducts > 1024 * RANK_E) CALL(1024, 2 * RANK_E);    \
+        else SB_RANK_SHAPES8(CALL);                                 \
     } while (0)
 
 void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
@@ -23,14 +29,14 @@ void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm,
 {
     if (count == 0) return;
     const float *nv = nullptr;
-#define SB_RANK_CNT(TH)                                                                                              \
-    launch_rank_rows<TH, RANK_E, float, RANK_COUNT>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax, \
+#define SB_RANK_CNT(TH, E)                                                                                              \
+    launch_rank_rows<TH, E, float, RANK_COUNT>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax, \
                                                     nullptr, nullptr, nullptr, rowNnz, nullptr, nullptr)
-#define SB_RANK_MAP(TH)                                                                                              \
-    launch_rank_rows<TH, RANK_E, float, RANK_MAP>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax,   \
+#define SB_RANK_MAP(TH, E)                                                                                              \
+    launch_rank_rows<TH, E, float, RANK_MAP>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax,   \
                                                   desc, aSeg, rankMap, rowNnz, nullptr, nullptr)
     if (desc && aSeg && rankMap) SB_RANK_SHAPES(SB_RANK_MAP);
-    else SB_RANK_SHAPES(SB_RANK_CNT);
+    else if (capProducts <= SORT_MAX_PRODUCTS) SB_RANK_SHAPES8(SB_RANK_CNT);   // larger rows: map only (capi.cu)
 #undef SB_RANK_CNT
 #undef SB_RANK_MAP
 }
@@ -42,10 +48,10 @@ void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, 
 {
     if (count == 0) return;
     u32 *rp = const_cast<u32 *>(cRp);
-#define SB_RANK_NUM(TH)                                                                                               \
-    launch_rank_rows<TH, RANK_E, T, RANK_NUMERIC>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax,   \
+#define SB_RANK_NUM(TH, E)                                                                                               \
+    launch_rank_rows<TH, E, T, RANK_NUMERIC>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax,   \
                                                   nullptr, nullptr, nullptr, rp, cCi, cV)
-    SB_RANK_SHAPES(SB_RANK_NUM);
+    if (capProducts <= SORT_MAX_PRODUCTS) SB_RANK_SHAPES8(SB_RANK_NUM);   // larger rows: map only (capi.cu)
 #undef SB_RANK_NUM
 }
 
@@ -55,8 +61,10 @@ void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc 
                             T *cV)
 {
     if (count == 0) return;
-#define SB_MAP_NUM(TH) launch_map_rows_cta<TH, RANK_E, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
-    SB_RANK_SHAPES(SB_MAP_NUM);
+#define SB_MAP_NUM(TH, E) launch_map_rows_cta<TH, E, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
+    if (capProducts <= 32 * RANK_E) SB_MAP_NUM(32, RANK_E);
+    else if (capProducts <= 64 * RANK_E) SB_MAP_NUM(64, RANK_E);
+    else SB_RANK_SHAPES(SB_MAP_NUM);
 #undef SB_MAP_NUM
 }
 

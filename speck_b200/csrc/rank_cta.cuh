@@ -376,8 +376,11 @@ struct MapCtaLayout {
     static constexpr size_t SMEM = STAB + al(CAP / 32 * 2);
 };
 
+#ifndef SB_MAP_CTA_THREADS_PER_SM
+#define SB_MAP_CTA_THREADS_PER_SM 1536
+#endif
 template <int THREADS, int E, typename T>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, SB_MAP_CTA_THREADS_PER_SM / THREADS)
 k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg, const T *__restrict__ aV,
                const u32 *__restrict__ bCi, const T *__restrict__ bV, const unsigned short *__restrict__ rankMap,
                u32 *__restrict__ cCi, T *__restrict__ cV)

@@ -26,8 +26,8 @@ def test_uniform_random(ctx, n, d, seed):
     check_case(ctx, M.uniform_random(n, n, d, seed), what=f"uniform {n} {d}")
 
 
-@pytest.fixture(params=[(8192, 1, 1), (8192, 1, 0), (8192, 0, 1), (8192, 0, 0), (1024, 1, 1), (64, 1, 1), (64, 1, 0)],
-                ids=["8192-rank-map", "8192-rank", "8192-sort-map", "8192-sort", "1024-map", "64-map", "64"])
+@pytest.fixture(params=[(16384, 1, 1), (8192, 1, 0), (8192, 0, 1), (8192, 0, 0), (1024, 1, 1), (64, 1, 1), (64, 1, 0)],
+                ids=["16384-rank-map", "8192-rank", "8192-sort-map", "8192-sort", "1024-map", "64-map", "64"])
 def sort_max(ctx, request):
     """Run a case with the sort/bitmap switch at several places, with the rank classes on and off and with
     and without the symbolic->numeric rank map, so that every kernel family (lane-group sort, rank, CTA
@@ -36,7 +36,7 @@ def sort_max(ctx, request):
     ctx.set_option("rank_path", request.param[1])
     ctx.set_option("rank_map", request.param[2])
     yield request.param[0]
-    ctx.set_option("sort_max", 8192)
+    ctx.set_option("sort_max", 16384)
     ctx.set_option("rank_path", 1)
     ctx.set_option("rank_map", 1)
 
@@ -47,7 +47,7 @@ def test_rmat(ctx, sort_max, scale, ef):
     got, st = check_case(ctx, A, what=f"rmat{scale} sort_max={sort_max}")
     if sort_max <= 1024 and scale >= 13:
         assert ndense(st) > 0
-    if sort_max == 8192 and scale >= 15:
+    if sort_max >= 8192 and scale >= 15:
         assert st["class_rows"]["sort2048"] > 0 and st["class_rows"]["sort4096"] > 0
 
 
@@ -57,11 +57,10 @@ def test_rectangular(ctx):
     check_case(ctx, A, B, what="rectangular")
 
 
-def _rows_with_products(targets, cols=4096, seed=0):
+def _rows_with_products(targets, cols=4096, seed=0, nb=128):
     """A whose row i has exactly targets[i] products against a B with one entry... B row k has
     length k+1 (k < 64) so any product count can be composed; all columns distinct mod cols."""
     rng = np.random.default_rng(seed)
-    nb = 128
     # B: row k has k+1 random distinct columns
     br, bc = [], []
     for k in range(nb):
@@ -92,13 +91,15 @@ def test_class_boundaries(ctx, rank_map):
     for c in range(0, 12):
         b = 4 << c
         targets += [b - 1, b, b + 1]
-    targets += [1, 2, 3, 8255, 8256]
-    A, B = _rows_with_products(targets, cols=1 << 18)
+    targets += [1, 2, 3, 8255, 8256, 12345, 16383, 16384, 16385, 20000, 32896]
+    A, B = _rows_with_products(targets, cols=1 << 18, nb=256)
     try:
         got, st = check_case(ctx, A, B, what="class boundaries")
     finally:
         ctx.set_option("rank_map", 1)
-    assert ndense(st) >= 3
+    # 8193..16384 products: rank kernels when the rank map is on, else the bitmap path
+    assert ndense(st) >= (3 if rank_map else 9)
+    assert st["class_rows"]["sort16384"] == (6 if rank_map else 0)
     # CTA classes step by 512 products (2..16 warps): b-1 and b fall in sort{b}, b+1 in sort{b+512}
     for name in ("sort1024", "sort1536", "sort2048", "sort2560", "sort4096", "sort4608", "sort8192"):
         assert st["class_rows"][name] >= 1, name
@@ -258,7 +259,7 @@ def test_sort_max_option_routes_more_rows_to_dense(ctx):
         got, st = check_case(ctx, A, what="sort_max=64")
         assert st["class_rows"]["sort128"] == 0 and ndense(st) > 0
     finally:
-        ctx.set_option("sort_max", 8192)
+        ctx.set_option("sort_max", 16384)
 
 
 def test_rank_class_many_short_b_rows(ctx):
