@@ -23,12 +23,16 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     args = ap.parse_args()
     from bench import load_workload
     from speck_b200 import api
     import oracle
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     ctx = api.Context(0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     with open(args.out, "a") as fo:
         for w in args.workloads:
             A = load_workload(w, 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w])

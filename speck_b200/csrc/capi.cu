@@ -67,8 +67,11 @@ struct speck_ctx {
     u32 sortMax = RANK_MAX_PRODUCTS;  // rows with more products take the bitmap path (clamped per multiply)
     bool rankPath = true;     // rows of 513..8192 products: rank classes instead of the CTA sort classes
     int symStreams = NSIDE;   // side streams used by the symbolic phase (instruction-bound kernels overlap well)
-    int numStreams = 1;       // ... and by the numeric phase besides the bitmap kernel's own stream: the mapped
-                              // numeric kernels are memory-latency bound and run faster one after the other
+    int numStreams = 0;       // ... and by the numeric phase besides the bitmap kernel's own stream; 0 = automatic:
+                              // one stream for large multiplies (the mapped numeric kernels are memory-latency
+                              // bound and run faster one after the other: R-MAT scale 20 5.0 vs 6.2 ms), all
+                              // streams for small ones (launch-latency bound: webbase-like 0.24 vs 0.39 ms)
+    int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = 6;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
     bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
     u32 launches = 0;
@@ -190,7 +193,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
                    wantMap ? (uint2 *)c->aSeg.p : nullptr);
     launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (u32 *)c->mapLen.p : nullptr,
-                       useRank);
+                       useRank, c->mapMinClass);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     cudaEventRecord(c->evStage[1], c->main);
@@ -272,7 +275,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (!cnt) continue;
         LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
-                             rowOps, cRp, desc ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
+                             rowOps, cRp, (desc && sc >= c->mapMinClass) ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
     }
     join_streams(c);
     cudaEventRecord(c->evStage[2], c->main);
@@ -307,6 +310,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     T *cV = (T *)C->data;
 
     // ---- numeric
+    const int numStreams = c->numStreams ? c->numStreams : (s1.products >= (1ull << 27) ? 1 : NSIDE);
     cudaEventRecord(c->evStage[4], c->main);
     if (rankMap) launch_desc_numeric(lc, binStart[NUM_BINS], cRp, desc);
     fork_streams(c);
@@ -323,7 +327,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             const int b0 = rankGroupFirst[g], b1 = rankGroupFirst[g + 1];
             const u32 cnt = binStart[b1] - binStart[b0];
             if (!cnt) continue;
-            LaunchCtx ls{c->side[sidx++ % c->numStreams], c->smCount, &c->launches};
+            LaunchCtx ls{c->side[sidx++ % numStreams], c->smCount, &c->launches};
             if (g == RANK_GROUPS - 1 && !rankMap) {
                 launch_dense_numeric<T>(ls, false, perm + binStart[b0], cnt, &c->dSc->denseCounter[5], aRp, aCi, aV, bRp, bCi,
                                         bV, colsB, rowMin, rowMax, nullptr, cRp, cCi, cV);
@@ -339,17 +343,18 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
-        LaunchCtx ls{c->side[sidx++ % c->numStreams], c->smCount, &c->launches};
-        if (rankMap && sc < NUM_WARP_SORT && sc >= c->mapCtaMin)   // rows of <= 4 << sc products: 32 / 64 threads x 8 slots
+        LaunchCtx ls{c->side[sidx++ % numStreams], c->smCount, &c->launches};
+        const bool mapped = rankMap && sc < NUM_WARP_SORT && sc >= c->mapMinClass;
+        if (mapped && sc >= c->mapCtaMin)   // rows of <= 4 << sc products: 32 / 64 threads x 8 slots
             launch_map_numeric_cta<T>(ls, 4u << sc, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
-        else if (rankMap && sc < NUM_WARP_SORT)
+        else if (mapped)
             launch_map_numeric<T>(ls, sc, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
         else
             launch_sort_numeric<T>(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, aV,
                                    bRp, bCi, bV, rowOps, cRp, cCi, cV);
     }
     {
-        LaunchCtx ls{c->side[sidx++ % c->numStreams], c->smCount, &c->launches};
+        LaunchCtx ls{c->side[sidx++ % numStreams], c->smCount, &c->launches};
         launch_direct_numeric<T>(ls, perm + binStart[BIN_DIRECT], s1.binCount[BIN_DIRECT], aRp, aCi, aV, bRp, bCi, bV,
                                  cRp, cCi, cV);
     }
@@ -668,8 +673,13 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         return SPECK_OK;
     }
     if (!strcmp(key, "sym_streams") || !strcmp(key, "num_streams")) {
-        if (value < 1 || value > NSIDE) return fail(SPECK_ERR_INVALID, "%s must be in [1, %d]", key, NSIDE);
+        if (value < (key[0] == 's' ? 1 : 0) || value > NSIDE) return fail(SPECK_ERR_INVALID, "%s must be in [1, %d]", key, NSIDE);
         (key[0] == 's' ? c->symStreams : c->numStreams) = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "map_min_class")) {
+        if (value < 0 || value > NUM_WARP_SORT) return fail(SPECK_ERR_INVALID, "map_min_class must be in [0, %d]", NUM_WARP_SORT);
+        c->mapMinClass = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "map_cta_min")) {

@@ -101,9 +101,9 @@ void launch_build_desc(const LaunchCtx &lc, const u32 *perm, u32 count, const u3
                        const u32 *rowMin, const u32 *rowMax, const u64 *mapBase, RowDesc *desc);
 void launch_desc_numeric(const LaunchCtx &lc, u32 count, const u32 *cRp, RowDesc *desc);
 // mapLen (optional, rows + 1 entries): products of the row when its class records a rank map in the symbolic
-// phase (lane-group classes always, CTA classes when mapCta), else 0
+// phase (lane-group classes from mapMinClass on, CTA classes when mapCta), else 0
 void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
-                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta);
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta, int mapMinClass);
 void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trailing total slot */,
                  u64 *tileState, Scalars *sc);
 // exclusive scan of in[0..n-1) into 64-bit out[0..n) (out[n-1] = total, also stored in sc->mapTotal)

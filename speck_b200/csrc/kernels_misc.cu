@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
                                                      const u32 *__restrict__ rowMin,
                                                      const u32 *__restrict__ rowMax, u32 *__restrict__ perm,
                                                      Scalars *sc, u32 sortMax, u32 *__restrict__ mapLen,
-                                                     bool mapCta)
+                                                     bool mapCta, int mapMinClass)
 {
     __shared__ u32 sCnt[NUM_BINS];
     __shared__ u32 sBase[NUM_BINS];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
         bin = classify_row(ops, aRp[row + 1] - aRp[row], ops ? rowMax[row] - rowMin[row] + 1u : 0u, sortMax);
         if (bin >= 0) rank = atomicAdd(&sCnt[bin], 1u);
         if (mapLen) {
-            const bool mapped = bin >= BIN_SORT0 && (bin < BIN_SORT0 + NUM_WARP_SORT || (mapCta && bin < BIN_DENSE_LOCAL));
+            const bool mapped = bin >= BIN_SORT0 + mapMinClass && (bin < BIN_SORT0 + NUM_WARP_SORT || (mapCta && bin < BIN_DENSE_LOCAL));
             mapLen[row] = mapped ? ops : 0u;
         }
     }
@@ -151,11 +151,11 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
 }
 
 void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
-                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta)
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta, int mapMinClass)
 {
     if (rows == 0) return;
     k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, rowMin, rowMax, perm, sc, sortMax, mapLen,
-                                                             mapCta);
+                                                             mapCta, mapMinClass);
     ++*lc.launches;
 }
 
