@@ -1,9 +1,4 @@
-for v in 1 2 4; do
-echo "num_streams=$v"
-timeout 300 python profiles/compare_ref.py --no-ref --out gpurun_out/s2_cmp_s$v.jsonl --opt num_streams=$v econ_like circuit_like webbase_like cant_like banded_like > /dev/null 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-ref-gpu --e2e-steps 1 > gpurun_out/s2_b.json 2> gpurun_out/s2_b.err
 python -c "
-import json
-for l in open('gpurun_out/s2_cmp_s$v.jsonl'):
-    d=json.loads(l); o=d['ours']; print(' ', d['workload'], round(o['mean_ms'],3), {k:round(x,3) for k,x in o['stage_ms'].items()})"
-done
-timeout 120 bash profiles/launch_list.sh s2_webbase --no-ref-gpu --workload webbase_like --seed 3
+import json; d=json.load(open('gpurun_out/s2_b.json')); print(d['value'], d['ms_per_step'], d['stage_ms'], d['roofline']['frac'])"

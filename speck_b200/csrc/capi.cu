@@ -72,7 +72,7 @@ struct speck_ctx {
                               // bound and run faster one after the other: R-MAT scale 20 5.0 vs 6.2 ms), all
                               // streams for small ones (launch-latency bound: webbase-like 0.24 vs 0.39 ms)
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
-    int mapCtaMin = 6;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
+    int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
     bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
     u32 launches = 0;
     speck_stats stats = {};

@@ -182,28 +182,44 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
             if ((int)l >= d) incl += t;
         }
         const u32 total = __shfl_sync(gmask, incl, G - 1, G);
-        for (u32 p0 = 0; p0 < total; p0 += G) {
-            const u32 p = p0 + l;
-            u32 lo = 0;
+        const u32 qb = bs - (incl - len);   // position in B of product p of this entry = qb + p
+        // U products per lane and iteration (whole-warp groups only): owners first, then all loads, then the stores
+        constexpr int U = (G == 32 && E >= 4) ? 4 : 1;
+        for (u32 p0 = 0; p0 < total; p0 += U * G) {
+            u32 q[U], col[U];
+            T oAv[U], bv[U];
 #pragma unroll
-            for (int s = G / 2; s >= 1; s >>= 1) {
-                const u32 v = __shfl_sync(gmask, incl, lo + s - 1, G);
-                if (v <= p) lo += s;
+            for (int u = 0; u < U; ++u) {
+                if (u > 0 && p0 + u * G >= total) break;   // group-uniform
+                const u32 p = p0 + u * G + l;
+                u32 lo = 0;
+#pragma unroll
+                for (int s = G / 2; s >= 1; s >>= 1) {
+                    const u32 v = __shfl_sync(gmask, incl, lo + s - 1, G);
+                    if (v <= p) lo += s;
+                }
+                q[u] = __shfl_sync(gmask, qb, lo, G) + p;
+                if (NUMERIC) oAv[u] = __shfl_sync(gmask, av, lo, G);
             }
-            const u32 oIncl = __shfl_sync(gmask, incl, lo, G);
-            const u32 oLen = __shfl_sync(gmask, len, lo, G);
-            const u32 oBs = __shfl_sync(gmask, bs, lo, G);
-            T oAv = (T)0;
-            if (NUMERIC) oAv = __shfl_sync(gmask, av, lo, G);
-            if (p < total) {
-                const u32 q = oBs + (p - (oIncl - oLen));
-                const u32 col = __ldg(bCi + q);
-                const u32 gp = base + p;
-                if (IDXKEYS) {
-                    keys[gp] = ((KeyT)col << IDXBITS) | (KeyT)gp;
-                    if (NUMERIC) vals[gp] = oAv * __ldg(bV + q);
-                } else {
-                    keys[gp] = (KeyT)col;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u > 0 && p0 + u * G >= total) break;
+                const bool ok = p0 + u * G + l < total;
+                col[u] = ok ? __ldg(bCi + q[u]) : 0u;
+                if (NUMERIC) bv[u] = ok ? __ldg(bV + q[u]) : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u > 0 && p0 + u * G >= total) break;
+                const u32 p = p0 + u * G + l;
+                if (p < total) {
+                    const u32 gp = base + p;
+                    if (IDXKEYS) {
+                        keys[gp] = ((KeyT)col[u] << IDXBITS) | (KeyT)gp;
+                        if (NUMERIC) vals[gp] = oAv[u] * bv[u];
+                    } else {
+                        keys[gp] = (KeyT)col[u];
+                    }
                 }
             }
         }
@@ -396,30 +412,47 @@ k_map_rows(const RowDesc *__restrict__ desc, const u32 count, const uint2 *__res
             if ((int)l >= d) incl += t;
         }
         const u32 total = __shfl_sync(gmask, incl, G - 1, G);
-        for (u32 p0 = 0; p0 < total; p0 += G) {
-            const u32 p = p0 + l;
-            u32 lo = 0;
+        const u32 qb = bs - (incl - len);   // position in B of product p of this entry = qb + p
+        // U products per lane and iteration (whole-warp groups only): owners first, then all loads, then the stores
+        constexpr int U = (G == 32 && N >= 128) ? 4 : 1;
+        for (u32 p0 = 0; p0 < total; p0 += U * G) {
+            u32 q[U], col[U], code[U];
+            T oAv[U], bv[U];
 #pragma unroll
-            for (int s = G / 2; s >= 1; s >>= 1) {
-                const u32 v = __shfl_sync(gmask, incl, lo + s - 1, G);
-                if (v <= p) lo += s;
+            for (int u = 0; u < U; ++u) {
+                if (u > 0 && p0 + u * G >= total) break;   // group-uniform
+                const u32 p = p0 + u * G + l;
+                u32 lo = 0;
+#pragma unroll
+                for (int s = G / 2; s >= 1; s >>= 1) {
+                    const u32 v = __shfl_sync(gmask, incl, lo + s - 1, G);
+                    if (v <= p) lo += s;
+                }
+                q[u] = __shfl_sync(gmask, qb, lo, G) + p;
+                oAv[u] = __shfl_sync(gmask, av, lo, G);
             }
-            const u32 oIncl = __shfl_sync(gmask, incl, lo, G);
-            const u32 oLen = __shfl_sync(gmask, len, lo, G);
-            const u32 oBs = __shfl_sync(gmask, bs, lo, G);
-            const T oAv = __shfl_sync(gmask, av, lo, G);
-            if (p < total) {
-                const u32 q = oBs + (p - (oIncl - oLen));
-                const u32 code = map[base + p];
-                const u32 col = __ldg(bCi + q);
-                const T pr = oAv * __ldg(bV + q);
-                const u32 r = code & MAP_RANK_MASK;
-                if (!folds) {
-                    outVal[r] = pr;
-                    outCol[r] = col;
-                } else {
-                    if (!(code & MAP_DUP)) outCol[r] = col;
-                    atomicAdd(&outVal[r], pr);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u > 0 && p0 + u * G >= total) break;
+                const u32 p = p0 + u * G + l;
+                const bool ok = p < total;
+                code[u] = ok ? (u32)map[base + p] : 0u;
+                col[u] = ok ? __ldg(bCi + q[u]) : 0u;
+                bv[u] = ok ? __ldg(bV + q[u]) : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u > 0 && p0 + u * G >= total) break;
+                if (p0 + u * G + l < total) {
+                    const T pr = oAv[u] * bv[u];
+                    const u32 r = code[u] & MAP_RANK_MASK;
+                    if (!folds) {
+                        outVal[r] = pr;
+                        outCol[r] = col[u];
+                    } else {
+                        if (!(code[u] & MAP_DUP)) outCol[r] = col[u];
+                        atomicAdd(&outVal[r], pr);
+                    }
                 }
             }
         }
