@@ -377,7 +377,7 @@ def main():
             "stage_ms": {"analysis": float(np.mean(ana_ms)), "symbolic": float(np.mean(sym_ms)),
                          "scan": float(np.mean(scan_ms)), "numeric": float(np.mean(num_ms)),
                          "wall_per_step": wall_ms / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "numeric phase (k_dense_rows + k_sort_rows + k_direct, concurrent)",
+            "roofline": {"bound": "hbm", "kernel": "numeric phase = one launch group: k_map_rows_cta (rows of 513..16384 products) + k_map_rows (<= 512) + k_dense_rows + k_direct",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "algorithmic_bytes": nb, "peak_source": peak_src},
             "e2e": {"value": 2.0 * P_all * args.e2e_steps / e2e_s / 1e9, "unit": "GFLOPS",
