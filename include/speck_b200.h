@@ -132,9 +132,18 @@ int speck_b200_synchronize(speck_ctx *ctx);
 /* The context's main stream as a cudaStream_t (void* to keep this header CUDA-free). */
 void *speck_b200_stream(speck_ctx *ctx);
 
-/* Tuning knobs (integers): "sort_max" = largest row-product count handled by the register-sort
- * classes (power of two in [4, 8192]; rows with more products take the bitmap path);
- * "release_workspace" = 1 frees the pooled workspace now. */
+/* Tuning knobs (integers; the defaults are the measured best, the switches exist so that the
+ * tests can drive every kernel family over the same inputs):
+ *   "sort_max"          largest row-product count handled by the sort / rank classes (power of two or
+ *                       multiple of 512 in [4, 16384]; rows with more products take the bitmap path)
+ *   "rank_path"         1 (default): rows of 513..16384 products use the bitmap-rank kernels,
+ *                       0: the CTA bitonic-sort kernels (always used when cols(B) > 2^20)
+ *   "rank_map"          1 (default): the symbolic phase records every product's sorted position
+ *                       (2 B per product of workspace) and the numeric phase only gathers and scatters,
+ *                       0: self-contained numeric kernels
+ *   "sym_streams", "num_streams"   side streams of the two phases (1..4; num_streams 0 = automatic)
+ *   "map_min_class", "map_cta_min" which lane-group classes use the rank map / the CTA map kernel
+ *   "release_workspace" 1 frees the pooled workspace now. */
 int speck_b200_set_option(speck_ctx *ctx, const char *key, long long value);
 
 #ifdef __cplusplus
