@@ -154,8 +154,10 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // CTA-level sort classes (> 1024 products) are used only while (col << log2 N) fits a u32 key;
     // wider matrices send those rows to the bitmap path instead of sorting u64 keys.
     u32 sortMax = c->sortMax;
-    const bool useRank = c->rankPath && colsB <= RANK_EXTENT_LIMIT;  // rank classes have no key-width limit
     const bool wantMap = c->rankMapOn;
+    // rank classes (no key-width limit): two bitmap levels up to 2^20 columns, three up to 2^25 (mapped only)
+    const int rankLevels = colsB <= RANK_EXTENT_LIMIT ? 2 : 3;
+    const bool useRank = c->rankPath && (rankLevels == 2 || (colsB <= RANK_EXTENT_LIMIT3 && wantMap));
     if (!(useRank && wantMap) && sortMax > SORT_MAX_PRODUCTS) sortMax = SORT_MAX_PRODUCTS;  // 8193..16384: mapped rank kernels only
     if (sortMax > 1024 && !useRank) {  // largest power-of-two network whose keys fit 32 bits: cols * N <= 2^32
         u32 fit = 8192;
@@ -267,7 +269,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
                 continue;
             }
             launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp,
-                                 desc ? desc + binStart[b0] : nullptr, aSeg, rankMap);
+                                 desc ? desc + binStart[b0] : nullptr, aSeg, rankMap, rankLevels);
         }
     }
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
@@ -335,9 +337,13 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             }
             if (rankMap)
                 launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
-            else
+            else if (rankLevels == 2)
                 launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
                                        rowMax, cRp, cCi, cV);
+            else  // wide matrix and no rank map: CTA bitonic classes with 64-bit keys
+                for (int b = b0; b < b1; ++b)
+                    launch_sort_numeric<T>(ls, b - BIN_SORT0, sort_keys_wide(b - BIN_SORT0, colsB), perm + binStart[b],
+                                           s1.binCount[b], aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV);
         }
     }
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {

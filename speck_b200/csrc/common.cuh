@@ -139,12 +139,14 @@ void launch_direct_numeric(const LaunchCtx &lc, const u32 *perm, u32 count, cons
                            const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *cRp,
                            u32 *cCi, T *cV);
 
-// rank classes (rank_cta.cuh): the CTA sort classes' rows when cols(B) <= RANK_EXTENT_LIMIT
+// rank classes (rank_cta.cuh): the CTA sort classes' rows when cols(B) <= RANK_EXTENT_LIMIT (two bitmap levels)
+// or <= RANK_EXTENT_LIMIT3 (three levels; symbolic kernels only, i.e. together with the rank map)
 constexpr u32 RANK_EXTENT_LIMIT = 1u << 20;
+constexpr u32 RANK_EXTENT_LIMIT3 = 1u << 25;
 void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                           const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, const u32 *rowMin,
                           const u32 *rowMax, u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg,
-                          unsigned short *rankMap);
+                          unsigned short *rankMap, int levels /* 2: cols(B) <= 2^20, 3: <= 2^25 */);
 template <typename T>
 void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,

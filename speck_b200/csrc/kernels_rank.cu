@@ -25,10 +25,21 @@ constexpr int RANK_E = 8;
 void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                           const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, const u32 *rowMin,
                           const u32 *rowMax, u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg,
-                          unsigned short *rankMap)
+                          unsigned short *rankMap, int levels)
 {
     if (count == 0) return;
     const float *nv = nullptr;
+#define SB_RANK_CNT3(TH, E)                                                                                             \
+    launch_rank_rows<TH, E, float, RANK_COUNT, 3>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax,  \
+                                                  nullptr, nullptr, nullptr, rowNnz, nullptr, nullptr)
+#define SB_RANK_MAP3(TH, E)                                                                                             \
+    launch_rank_rows<TH, E, float, RANK_MAP, 3>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax,    \
+                                                desc, aSeg, rankMap, rowNnz, nullptr, nullptr)
+    if (levels == 3) {   // cols(B) in (2^20, 2^25]
+        if (desc && aSeg && rankMap) SB_RANK_SHAPES(SB_RANK_MAP3);
+        else if (capProducts <= SORT_MAX_PRODUCTS) SB_RANK_SHAPES8(SB_RANK_CNT3);
+        return;
+    }
 #define SB_RANK_CNT(TH, E)                                                                                              \
     launch_rank_rows<TH, E, float, RANK_COUNT>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax, \
                                                     nullptr, nullptr, nullptr, rowNnz, nullptr, nullptr)
@@ -39,6 +50,8 @@ void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm,
     else if (capProducts <= SORT_MAX_PRODUCTS) SB_RANK_SHAPES8(SB_RANK_CNT);   // larger rows: map only (capi.cu)
 #undef SB_RANK_CNT
 #undef SB_RANK_MAP
+#undef SB_RANK_CNT3
+#undef SB_RANK_MAP3
 }
 
 template <typename T>

@@ -25,7 +25,8 @@
 namespace sb {
 
 constexpr int RANK_TOP_WORDS = 1024;
-constexpr u32 RANK_MAX_EXTENT = 1u << 20;   // RANK_TOP_WORDS * 32 * 32 columns
+constexpr u32 RANK_MAX_EXTENT = 1u << 20;    // two levels: RANK_TOP_WORDS * 32 * 32 columns
+constexpr u32 RANK_MAX_EXTENT3 = 1u << 25;   // three levels
 
 // exclusive scan of one u32 per thread over a CTA of THREADS threads; sWarp: 33 words.
 // Contains two barriers; *total = block sum.
@@ -91,7 +92,7 @@ struct SegWalk {
 //   outVal[CAP] T | sAv[THREADS] T | top[1024] | topPre[1024] u16 | leaf[CAP] | leafPre[CAP] u16 |
 //   leafId[CAP] u16 | sIncl[THREADS] | sBs[THREADS] | sTab[CAP/32] u16 | outCol[CAP] (numeric; aliased onto
 //   top/topPre when it fits: both are dead once the leaf words are filled)
-template <int THREADS, int E, typename T, bool NUMERIC>
+template <int THREADS, int E, typename T, bool NUMERIC, int LEVELS = 2>
 struct RankLayout {
     static constexpr size_t al(size_t b) { return (b + 15) / 16 * 16; }
     static constexpr size_t CAP = (size_t)THREADS * E;
@@ -103,7 +104,9 @@ struct RankLayout {
     static constexpr size_t LEAF = TOPPRE + RANK_TOP_WORDS * 2;
     static constexpr size_t LEAFPRE = LEAF + al(CAP * 4);
     static constexpr size_t LEAFID = LEAFPRE + al(CAP * 2);
-    static constexpr size_t SINCL = LEAFID + (NUMERIC ? al(CAP * 2) : 0);
+    static constexpr size_t MID = LEAFID + (NUMERIC ? al(CAP * 2) : 0);        // LEVELS == 3: mid words + prefixes
+    static constexpr size_t MIDPRE = MID + (LEVELS == 3 ? al(CAP * 4) : 0);
+    static constexpr size_t SINCL = MIDPRE + (LEVELS == 3 ? al(CAP * 2) : 0);
     static constexpr size_t SBS = SINCL + al(THREADS * 4);
     static constexpr size_t STAB = SBS + al(THREADS * 4);
     static constexpr size_t OUTCOL = (NUMERIC && COL_ALIASED) ? TOP : STAB + al(CAP / 32 * 2);
@@ -148,7 +151,7 @@ __device__ __forceinline__ u32 rank_scan_level(const u32 *bits, unsigned short *
 enum { RANK_COUNT = 0, RANK_NUMERIC = 1, RANK_MAP = 2 };
 
 // the mapped symbolic kernel is instruction-bound: full occupancy (32 registers) measured best
-template <int THREADS, int E, typename T, int MODE>
+template <int THREADS, int E, typename T, int MODE, int LEVELS>
 __global__ void __launch_bounds__(THREADS, (MODE == RANK_MAP && E <= 8) ? 2048 / THREADS : 1)
 k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32 *__restrict__ aCi,
             const T *__restrict__ aV, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
@@ -158,7 +161,9 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
 {
     constexpr bool NUMERIC = MODE == RANK_NUMERIC;
     constexpr bool DESC = MODE == RANK_MAP;   // row parameters from the descriptor, B-row bounds from aSeg
-    using L = RankLayout<THREADS, E, T, NUMERIC>;
+    static_assert(LEVELS == 2 || (LEVELS == 3 && !NUMERIC), "three levels: symbolic modes only");
+    constexpr int TOPSHIFT = 5 * LEVELS;      // column bits below a top word
+    using L = RankLayout<THREADS, E, T, NUMERIC, LEVELS>;
     constexpr u32 NONE = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     T *outVal = reinterpret_cast<T *>(smemRaw + L::OUTVAL);
@@ -168,6 +173,8 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     u32 *leaf = reinterpret_cast<u32 *>(smemRaw + L::LEAF);
     unsigned short *leafPre = reinterpret_cast<unsigned short *>(smemRaw + L::LEAFPRE);
     unsigned short *leafId = reinterpret_cast<unsigned short *>(smemRaw + L::LEAFID);
+    u32 *mid = reinterpret_cast<u32 *>(smemRaw + L::MID);
+    unsigned short *midPre = reinterpret_cast<unsigned short *>(smemRaw + L::MIDPRE);
     u32 *sIncl = reinterpret_cast<u32 *>(smemRaw + L::SINCL);
     u32 *sBs = reinterpret_cast<u32 *>(smemRaw + L::SBS);
     unsigned short *sTab = reinterpret_cast<unsigned short *>(smemRaw + L::STAB);
@@ -189,7 +196,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         aBeg = aRp[row]; aEnd = aRp[row + 1];
         cmin = rowMin[row]; cmax = rowMax[row];
     }
-    const u32 topWords = ((cmax - cmin) >> 10) + 1;          // <= RANK_TOP_WORDS: the host checks cols(B)
+    const u32 topWords = ((cmax - cmin) >> TOPSHIFT) + 1;    // <= RANK_TOP_WORDS: the host checks cols(B)
     u32 cBase = 0, nnzRow = 0;
     if (NUMERIC) {
         cBase = cRp[row];
@@ -264,7 +271,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
                     const u32 c = cc[u] - cmin;
                     col[i0 + u] = c;
                     if (NUMERIC) prod[i0 + u] = av[u] * bv[u];
-                    atomicOr(&top[c >> 10], 1u << ((c >> 5) & 31));
+                    atomicOr(&top[c >> TOPSHIFT], 1u << ((c >> (TOPSHIFT - 5)) & 31));
                 }
             }
         }
@@ -272,8 +279,33 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         __syncthreads();
     }
 
+    // ---------------------------------------------------------------- (three levels) mid words of the touched
+    // 1024-column blocks: same step as the leaf level below, one digit higher
+    u32 upperWords = topWords;   // words of the level above the leaves
+    if (LEVELS == 3) {
+        const u32 mids = rank_scan_level<THREADS, true>(top, topPre, topWords, sWarp);
+#pragma unroll 1
+        for (u32 j = tid; j < (mids + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(mid)[j] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if ((u32)i >= EP) break;
+            if (col[i] != NONE) {
+                const u32 c = col[i];
+                const u32 tw = c >> 15, tb = (c >> 10) & 31;
+                const u32 ms = topPre[tw] + __popc(top[tw] & ((1u << tb) - 1u));
+                atomicOr(&mid[ms], 1u << ((c >> 5) & 31));
+                col[i] = (ms << 10) | (c & 1023u);   // mid slot (< 2^14) and the two low digits
+            }
+        }
+        __syncthreads();
+        upperWords = mids;
+    }
+    const u32 *upper = LEVELS == 3 ? mid : top;
+    unsigned short *upperPre = LEVELS == 3 ? midPre : topPre;
+
     // ---------------------------------------------------------------- leaf words of the touched chunks
-    const u32 leaves = rank_scan_level<THREADS, true>(top, topPre, topWords, sWarp);
+    const u32 leaves = rank_scan_level<THREADS, true>(upper, upperPre, upperWords, sWarp);
 #pragma unroll 1
     for (u32 j = tid; j < (leaves + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(leaf)[j] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -283,8 +315,8 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         if ((u32)i >= EP) break;
         if (col[i] != NONE) {
             const u32 c = col[i];
-            const u32 tw = c >> 10, tb = (c >> 5) & 31;
-            const u32 s = topPre[tw] + __popc(top[tw] & ((1u << tb) - 1u));
+            const u32 tw = c >> 10, tb = (c >> 5) & 31;   // word / bit in the level above (three levels: mid slot)
+            const u32 s = upperPre[tw] + __popc(upper[tw] & ((1u << tb) - 1u));
             const u32 bit = 1u << (c & 31);
             const u32 old = atomicOr(&leaf[s], bit);
             if (MODE != RANK_COUNT && (old & bit)) dup |= 1u << i;
@@ -345,14 +377,14 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     }
 }
 
-template <int THREADS, int E, typename T, int MODE>
+template <int THREADS, int E, typename T, int MODE, int LEVELS = 2>
 void launch_rank_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                       const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, const u32 *rowMin,
                       const u32 *rowMax, const RowDesc *desc, const uint2 *aSeg, unsigned short *rankMap, u32 *cRp,
                       u32 *cCi, T *cV)
 {
-    using L = RankLayout<THREADS, E, T, MODE == RANK_NUMERIC>;
-    auto kern = k_rank_rows<THREADS, E, T, MODE>;
+    using L = RankLayout<THREADS, E, T, MODE == RANK_NUMERIC, LEVELS>;
+    auto kern = k_rank_rows<THREADS, E, T, MODE, LEVELS>;
     if (L::SMEM > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
     kern<<<count, THREADS, L::SMEM, lc.stream>>>(perm, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin, rowMax, desc, aSeg,

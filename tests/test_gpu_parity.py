@@ -295,3 +295,29 @@ def test_rank_class_duplicates_over_wide_extent(ctx):
     got, st = check_case(ctx, A, B, what="rank duplicates")
     assert st["products"] > 5 * st["nnz_c"]
     assert sum(st["class_rows"][f"sort{512 * w}"] for w in range(2, 17)) > 32
+
+
+@pytest.mark.parametrize("cols", [(1 << 24) + 7, 1 << 25, (1 << 25) + 1])
+def test_rank_three_levels_wide_columns(ctx, cols):
+    """cols(B) in (2^20, 2^25]: rank kernels with a third bitmap level (symbolic) + mapped numeric; one column
+    past 2^25 the CTA sort / bitmap-window fallbacks take over.  Rows of ~600..16000 products, with folding
+    (B rows share a column pool) and columns at both ends of the range."""
+    rng = np.random.default_rng(41)
+    nb = 1500
+    pool = np.unique(np.concatenate([[0, cols - 1], rng.integers(0, cols, 60000)]))
+    br, bc = [], []
+    for k in range(nb):
+        ln = int(rng.integers(1, 60))
+        br += [k] * ln
+        bc += list(rng.choice(pool, ln, replace=False))
+    B = M.from_coo(nb, cols, br, bc, seed=42)
+    ar, ac = [], []
+    for i, alen in enumerate([20, 40, 70, 100, 140, 200, 280, 400, 520]):
+        ar += [i] * alen
+        ac += list(rng.choice(nb, alen, replace=False))
+    A = M.from_coo(9, nb, ar, ac, seed=43)
+    got, st = check_case(ctx, A, B, what=f"three levels cols={cols}")
+    cta = sum(st["class_rows"][f"sort{512 * w}"] for w in range(2, 17)) + st["class_rows"]["sort16384"]
+    if cols <= (1 << 25):
+        assert cta >= 6 and st["class_rows"]["sort16384"] >= 1
+    assert st["nnz_c"] < st["products"]
