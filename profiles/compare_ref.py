@@ -35,8 +35,8 @@ def main():
         ctx.set_option(k, int(v))
     with open(args.out, "a") as fo:
         for w in args.workloads:
-            A = load_workload(w, 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w])
-            seed = 20 if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w]
+            A = load_workload(w, (24 if w == "rmat24" else 20) if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w])
+            seed = (24 if w == "rmat24" else 20) if w.startswith("rmat") else {"webbase_like": 3, "cant_like": 44, "banded_like": 41, "econ_like": 42, "circuit_like": 43}[w]
             dA = ctx.upload(A)
             dC = api.DeviceCSR(ctx)
             for _ in range(args.warmup):

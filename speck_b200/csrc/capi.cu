@@ -71,6 +71,7 @@ struct speck_ctx {
                               // one stream for large multiplies (the mapped numeric kernels are memory-latency
                               // bound and run faster one after the other: R-MAT scale 20 5.0 vs 6.2 ms), all
                               // streams for small ones (launch-latency bound: webbase-like 0.24 vs 0.39 ms)
+    size_t rankMapMaxBytes = ~(size_t)0;  // test hook: larger maps are treated as "does not fit" (exercises the fallbacks)
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
     bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
@@ -232,8 +233,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     const uint2 *aSeg = nullptr;
     if (wantMap && s1.mapTotal) {
         const size_t need = (size_t)s1.mapTotal * 2;
-        bool fits = need <= c->rankMap.cap;
-        if (!fits) {  // grow only while it leaves at least half of the free memory to C
+        bool fits = need <= c->rankMap.cap && need <= c->rankMapMaxBytes;
+        if (!fits && need <= c->rankMapMaxBytes) {  // grow only while it leaves at least half of the free memory to C
             size_t freeB = 0, totalB = 0;
             cudaMemGetInfo(&freeB, &totalB);
             fits = need < (freeB + c->rankMap.cap) / 2;
@@ -681,6 +682,10 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "sym_streams") || !strcmp(key, "num_streams")) {
         if (value < (key[0] == 's' ? 1 : 0) || value > NSIDE) return fail(SPECK_ERR_INVALID, "%s must be in [1, %d]", key, NSIDE);
         (key[0] == 's' ? c->symStreams : c->numStreams) = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "rank_map_max_bytes")) {
+        c->rankMapMaxBytes = value < 0 ? ~(size_t)0 : (size_t)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "map_min_class")) {

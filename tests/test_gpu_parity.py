@@ -321,3 +321,20 @@ def test_rank_three_levels_wide_columns(ctx, cols):
     if cols <= (1 << 25):
         assert cta >= 6 and st["class_rows"]["sort16384"] >= 1
     assert st["nnz_c"] < st["products"]
+
+
+@pytest.mark.parametrize("cols", [1 << 18, (1 << 24) + 7])
+def test_rank_map_allocation_fallback(ctx, cols):
+    """Rows are binned for the mapped kernels (up to 16384 products, three bitmap levels for wide matrices), then
+    the rank map "does not fit": the 16384 bin must fall back to the bitmap kernel, the other CTA bins to the
+    self-contained rank kernels (two levels) or the 64-bit-key CTA sort (three levels)."""
+    targets = [600, 1500, 3000, 5000, 8192, 9000, 16384, 100, 30]
+    A, B = _rows_with_products(targets, cols=cols, nb=256, seed=5)
+    ctx.set_option("rank_map_max_bytes", 1)
+    try:
+        got, st = check_case(ctx, A, B, what=f"map fallback cols={cols}")
+    finally:
+        ctx.set_option("rank_map_max_bytes", -1)
+    assert st["class_rows"]["sort16384"] == 2
+    got2, st2 = check_case(ctx, A, B, what=f"mapped cols={cols}")
+    assert_csr_equal(got, got2, what="fallback vs mapped")
