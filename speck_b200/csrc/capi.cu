@@ -277,8 +277,15 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
         if (!cnt) continue;
         LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
-        launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
-                             rowOps, cRp, (desc && sc >= c->mapMinClass) ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
+        const bool mapped = desc && sc >= c->mapMinClass;
+        // 64-bit sort keys cost 2-3x (R-MAT scale 24: 28 ps per product in the 512 class): wide matrices rank these
+        // rows with the three-level bitmap kernel (u32 throughout) instead
+        if (mapped && useRank && rankLevels == 3 && sc >= 6 && sc < NUM_WARP_SORT && sort_keys_wide(sc, colsB))
+            launch_rank_symbolic(ls, 4u << sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax,
+                                 cRp, desc + binStart[BIN_SORT0 + sc], aSeg, rankMap, 3);
+        else
+            launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
+                                 rowOps, cRp, mapped ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
     }
     join_streams(c);
     cudaEventRecord(c->evStage[2], c->main);

@@ -36,7 +36,10 @@ void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm,
     launch_rank_rows<TH, E, float, RANK_MAP, 3>(lc, perm, count, aRp, aCi, nv, bRp, bCi, nv, rowOps, rowMin, rowMax,    \
                                                 desc, aSeg, rankMap, rowNnz, nullptr, nullptr)
     if (levels == 3) {   // cols(B) in (2^20, 2^25]
-        if (desc && aSeg && rankMap) SB_RANK_SHAPES(SB_RANK_MAP3);
+        // lane-group classes of 256 / 512 products whose bitonic sort would need 64-bit keys (capi.cu)
+        if (desc && aSeg && rankMap && capProducts <= 32 * RANK_E) SB_RANK_MAP3(32, RANK_E);
+        else if (desc && aSeg && rankMap && capProducts <= 64 * RANK_E) SB_RANK_MAP3(64, RANK_E);
+        else if (desc && aSeg && rankMap) SB_RANK_SHAPES(SB_RANK_MAP3);
         else if (capProducts <= SORT_MAX_PRODUCTS) SB_RANK_SHAPES8(SB_RANK_CNT3);
         return;
     }

@@ -152,7 +152,7 @@ enum { RANK_COUNT = 0, RANK_NUMERIC = 1, RANK_MAP = 2 };
 
 // the mapped symbolic kernel is instruction-bound: full occupancy (32 registers) measured best
 template <int THREADS, int E, typename T, int MODE, int LEVELS>
-__global__ void __launch_bounds__(THREADS, (MODE == RANK_MAP && E <= 8) ? 2048 / THREADS : 1)
+__global__ void __launch_bounds__(THREADS, (MODE == RANK_MAP && E <= 8) ? (2048 / THREADS > 32 ? 32 : 2048 / THREADS) : 1)
 k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32 *__restrict__ aCi,
             const T *__restrict__ aV, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
             const T *__restrict__ bV, const u32 *__restrict__ rowOps, const u32 *__restrict__ rowMin,
