@@ -1,6 +1,6 @@
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
-timeout 600 python profiles/compare_ref.py --no-ref --out gpurun_out/s2_cmp_rmat24b.jsonl --iters 5 --warmup 3 rmat24 > /dev/null 2>&1
+for v in 0 1 2; do
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-ref-gpu --e2e-steps 1 --opt map_prefetch=$v > gpurun_out/s2_v$v.json 2> gpurun_out/s2_v$v.err
 python -c "
-import json
-for l in open('gpurun_out/s2_cmp_rmat24b.jsonl'):
-    d=json.loads(l); o=d['ours']; print(' ', d['workload'], round(o['mean_ms'],3), round(o['gflops_mean'],1), {k:round(x,3) for k,x in o['stage_ms'].items()}, o['idx_bit_exact_vs_oracle'])"
+import json; d=json.load(open('gpurun_out/s2_v$v.json')); print('prefetch', $v, d['value'], d['ms_per_step'], d['stage_ms'], d['roofline']['frac'])"
+done

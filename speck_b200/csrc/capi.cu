@@ -59,7 +59,7 @@ struct speck_ctx {
     cudaEvent_t evStage[6] = {};
     Scalars *dSc = nullptr;
     Scalars *hSc = nullptr;  // pinned
-    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore, mapLen, mapBase, rankMap, aSeg, desc;
+    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore, mapLen, mapBase, rankMap, aSeg, desc, rowInfo;
     DevBuf stage[6];          // device staging of the *_host entry points (A: rp, ci, v; B: rp, ci, v)
     void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
     size_t hostOutCap[3] = {};
@@ -180,6 +180,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if ((rc = ensure(c->aSeg, (size_t)A->nnz * sizeof(uint2)))) return rc;
         if ((rc = ensure(c->desc, (size_t)rows * sizeof(RowDesc)))) return rc;
     }
+    if ((rc = ensure(c->rowInfo, (size_t)B->rows * sizeof(uint4)))) return rc;
     u32 *cRp = C->row_offsets;
     if (!(C->rows == A->rows && cRp != nullptr)) {
         if (cRp) cudaFree(cRp);
@@ -193,8 +194,9 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
 
     // ---- analysis + binning
+    launch_row_info(lc, (u32)B->rows, bRp, bCi, (uint4 *)c->rowInfo.p);
     launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
-                   wantMap ? (uint2 *)c->aSeg.p : nullptr);
+                   wantMap ? (uint2 *)c->aSeg.p : nullptr, (const uint4 *)c->rowInfo.p);
     launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (u32 *)c->mapLen.p : nullptr,
                        useRank, c->mapMinClass);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
@@ -391,7 +393,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
     cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
     st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->rowMin.cap + c->rowMax.cap + c->tileState.cap + c->bitmapStore.cap +
-                         c->mapLen.cap + c->mapBase.cap + c->rankMap.cap + c->aSeg.cap + c->desc.cap;
+                         c->mapLen.cap + c->mapBase.cap + c->rankMap.cap + c->aSeg.cap + c->desc.cap + c->rowInfo.cap;
     if (tm) {
         float allocMs = 0.f;
         cudaEventElapsedTime(&allocMs, c->evStage[3], c->evStage[4]);
@@ -541,7 +543,7 @@ int speck_b200_destroy(speck_ctx *c)
     if (!c) return SPECK_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc);
+    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc); release(c->rowInfo);
     for (auto &b : c->stage) release(b);
     for (auto &h : c->hostOut) if (h) cudaFreeHost(h);
     if (c->hostC.data) cudaFree(c->hostC.data);
@@ -607,7 +609,7 @@ int speck_b200_row_products(speck_ctx *c, const speck_csr *A, const speck_csr *B
     u32 n = 0;
     LaunchCtx lc{c->main, c->smCount, &n};
     launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, B->col_ids, (u32 *)c->rowOps.p,
-                   (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax, nullptr);
+                   (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax, nullptr, nullptr);
     if (dRowOps) CU_TRY(cudaMemcpyAsync(dRowOps, c->rowOps.p, (size_t)rows * 4, cudaMemcpyDeviceToDevice, c->main));
     CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     CU_TRY(cudaStreamSynchronize(c->main));
@@ -716,7 +718,7 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "release_workspace")) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc);
+        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc); release(c->rowInfo);
         for (auto &b : c->stage) release(b);
         return SPECK_OK;
     }

@@ -94,7 +94,9 @@ struct LaunchCtx {
 // kernels need one load level (aSeg) instead of two (A.col_ids -> B.row_offsets)
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg);
+                    uint2 *aSeg, const uint4 *rowInfo);
+// rowInfo[k] = (begin, end, first column, last column) of B row k: one gather per A entry in the analysis
+void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *bCi, uint4 *rowInfo);
 // descriptors of perm[0..count): symbolic flavour (c0/c1 = column extent), then switched to the numeric
 // flavour (c0/c1 = position / length in C) once row_offsets are scanned
 void launch_build_desc(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *rowOps,

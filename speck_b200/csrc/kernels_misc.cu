@@ -12,13 +12,37 @@ namespace sb {
 // Rows without products get rowNnz = 0 here; one-entry rows get rowNnz = nnz(B_k) (they
 // skip the symbolic phase, as directSpGEMMCount does, spECK_HashSpGEMM.cuh:572-589).
 // ------------------------------------------------------------------------------------------
+// Per-row summary of B: (begin, end, first column, last column) in one 16-byte entry, so that the analysis
+// gathers ONE sector per A entry instead of three (B.row_offsets pair, first and last column of the row).
+__global__ void __launch_bounds__(256) k_row_info(u32 rowsB, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
+                                                  uint4 *__restrict__ rowInfo)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= rowsB) return;
+    const u32 bs = bRp[k], be = bRp[k + 1];
+    uint4 ri = make_uint4(bs, be, 0xffffffffu, 0u);
+    if (be > bs) {
+        ri.z = __ldg(bCi + bs);
+        ri.w = __ldg(bCi + be - 1);
+    }
+    rowInfo[k] = ri;
+}
+
+void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *bCi, uint4 *rowInfo)
+{
+    if (rowsB == 0) return;
+    k_row_info<<<(rowsB + 255) / 256, 256, 0, lc.stream>>>(rowsB, bRp, bCi, rowInfo);
+    ++*lc.launches;
+}
+
 template <int LA>
 __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict__ aRp,
                                                  const u32 *__restrict__ aCi,
                                                  const u32 *__restrict__ bRp, const u32 *__restrict__ bCi,
                                                  u32 *__restrict__ rowOps, u32 *__restrict__ rowMin,
                                                  u32 *__restrict__ rowMax, u32 *__restrict__ rowNnz, Scalars *sc,
-                                                 u32 sortMax, uint2 *__restrict__ aSeg)
+                                                 u32 sortMax, uint2 *__restrict__ aSeg,
+                                                 const uint4 *__restrict__ rowInfo)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -40,13 +64,21 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
         aLen = end - beg;
         for (u32 p = beg + lane; p < end; p += LA) {
             const u32 k = __ldg(aCi + p);
-            const u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
+            u32 bs, be;
+            if (rowInfo) {
+                const uint4 ri = __ldg(rowInfo + k);
+                bs = ri.x; be = ri.y;
+                cmin = min(cmin, ri.z);   // empty rows carry (0xffffffff, 0)
+                cmax = max(cmax, ri.w);
+            } else {
+                bs = __ldg(bRp + k); be = __ldg(bRp + k + 1);
+                if (be > bs) {
+                    cmin = min(cmin, __ldg(bCi + bs));
+                    cmax = max(cmax, __ldg(bCi + be - 1));
+                }
+            }
             ops64 += (u64)(be - bs);
             if (aSeg) aSeg[p] = make_uint2(bs, be);
-            if (be > bs) {
-                cmin = min(cmin, __ldg(bCi + bs));
-                cmax = max(cmax, __ldg(bCi + be - 1));
-            }
         }
     }
 #pragma unroll
@@ -93,20 +125,20 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg)
+                    uint2 *aSeg, const uint4 *rowInfo)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
     const int threads = 256;
     if (avg <= 3.0) {
         const u32 grid = (u32)(((u64)rows * 2 + threads - 1) / threads);
-        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg);
+        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo);
     } else if (avg <= 24.0) {
         const u32 grid = (u32)(((u64)rows * 8 + threads - 1) / threads);
-        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg);
+        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo);
     } else {
         const u32 grid = (u32)(((u64)rows * 32 + threads - 1) / threads);
-        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg);
+        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo);
     }
     ++*lc.launches;
 }
