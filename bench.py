@@ -135,15 +135,14 @@ def cpu_sample(A: HostCSR, stride):
 
 
 def time_oracle(As: HostCSR, B: HostCSR, reps=1):
+    """mean seconds per multiply of the CPU oracle over `reps` repetitions (after one warm-up)"""
     import oracle
     _, _, P, _ = oracle.row_products(As.row_offsets, As.col_ids, B.row_offsets)
-    best = None
+    oracle.spgemm(As.row_offsets, As.col_ids, As.data, B.row_offsets, B.col_ids, B.data, B.cols)
+    t0 = time.perf_counter()
     for _ in range(reps):
-        t0 = time.perf_counter()
         oracle.spgemm(As.row_offsets, As.col_ids, As.data, B.row_offsets, B.col_ids, B.data, B.cols)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return P, best
+    return P, (time.perf_counter() - t0) / reps
 
 
 def time_reference_gpu(args):
@@ -179,7 +178,7 @@ def run_reference_arm(args, rank, world):
     oracle.build()
     A = load_workload(args.workload, args.seed)
     stride = args.cpu_stride
-    As = cpu_sample(A, stride)
+    As = cpu_sample(A, stride) if stride > 1 else A
     cores = oracle.num_threads()
     _, _, P, _ = oracle.row_products(As.row_offsets, As.col_ids, A.row_offsets)
     for _ in range(min(args.warmup, 1)):
@@ -189,7 +188,7 @@ def run_reference_arm(args, rank, world):
         oracle.spgemm(As.row_offsets, As.col_ids, As.data, A.row_offsets, A.col_ids, A.data, A.cols)
     dt = time.perf_counter() - t0
     gflops = 2.0 * P * args.steps / dt / 1e9
-    sample = f"every {stride}th row of A ({As.rows} rows, P={P}) x full B, per step"
+    sample = (f"every {stride}th row of A" if stride > 1 else "all rows of A") + f" ({As.rows} rows, P={P}) x full B, per step"
     line = {
         "impl": "reference", "metric": "SpGEMM GFLOPS (2*P/t), C=A.A", "value": gflops, "unit": "GFLOPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -210,7 +209,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rmat20")
     ap.add_argument("--seed", type=int, default=20)
-    ap.add_argument("--cpu-stride", type=int, default=4, help="row stride of the bounded CPU sample")
+    ap.add_argument("--cpu-stride", type=int, default=1, help="row stride of the bounded CPU sample (1 = the whole workload)")
+    ap.add_argument("--cpu-reps", type=int, default=5, help="repetitions of the CPU sample in the GPU arm (about 10 s in total)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true",
@@ -389,11 +389,12 @@ def main():
         if not args.no_cpu_baseline:
             import oracle
             oracle.build()
-            As = cpu_sample(A, args.cpu_stride)
-            Pc, tc = time_oracle(As, hostB)
+            As = cpu_sample(A, args.cpu_stride) if args.cpu_stride > 1 else A
+            Pc, tc = time_oracle(As, hostB, args.cpu_reps)
             line["cpu_baseline"] = {"value": 2.0 * Pc / tc / 1e9, "unit": "GFLOPS", "cores": oracle.num_threads(),
                                     "kind": "port",
-                                    "sample": f"every {args.cpu_stride}th row of A ({As.rows} rows, P={Pc}) x full B, {tc:.2f} s"}
+                                    "sample": (f"every {args.cpu_stride}th row of A" if args.cpu_stride > 1 else "all rows of A")
+                                    + f" ({As.rows} rows, P={Pc}) x full B, mean of {args.cpu_reps} runs of {tc:.2f} s"}
         if not args.no_ref_gpu and world == 1:
             line["ref_speck_gpu"] = time_reference_gpu(args)
         prof = os.path.join(ROOT, "profiles", "traffic.json")
