@@ -2,11 +2,12 @@
 //
 // Stage order and the reference stage each one replaces (source/GPU/Multiply.cu):
 //   analyze + bin      <- countProducts (:237-273) + loadBalanceCounting (:279-351)
-//   symbolic           <- globalMapsCounting + spGEMMCounting (:357-582), no global hash maps
+//   symbolic           <- globalMapsCounting + spGEMMCounting (:357-582), no global hash maps; also records the
+//                         rank map (sorted position of every product, 2 B each) for the numeric phase
 //   scan               <- cub::DeviceScan::ExclusiveSum (:570) + nnz read-back (:571-575)
 //   alloc C            <- allocC (:588-608), same reuse rules
-//   numeric            <- loadBalanceNumeric .. sorting (:614-1050); output is sorted in the
-//                         numeric kernels themselves, there is no separate sorting stage
+//   numeric            <- loadBalanceNumeric .. sorting (:614-1050); rows are written sorted, there is no
+//                         separate sorting stage and (with the rank map) no hashing or sorting at all
 // Host<->device traffic per call: two 4-byte-class read-backs of one pinned Scalars struct
 // (after binning, after the scan) instead of the reference's 3-8 blocking copies, and no
 // cudaMalloc/cudaFree in the steady state (pooled workspace).

@@ -1,18 +1,20 @@
 // speck_b200/csrc/common.cuh -- shared definitions of the sm_100a SpGEMM kernels.
 //
 // Pipeline (replaces source/GPU/Multiply.cu:99-1122 of the reference):
-//   analyze rows -> bin rows by product count -> symbolic (exact nnz per row) ->
-//   decoupled look-back scan (row_ptr) -> numeric (sorted col/val assembly).
+//   B row summary -> analyze rows -> bin rows by product count -> rank-map offsets + row descriptors ->
+//   symbolic (exact nnz per row + the rank map: sorted position of every product) ->
+//   decoupled look-back scan (row_ptr) -> numeric (gather, multiply, scatter by rank, coalesced row writes).
 // Row classes ("bins"):
 //   BIN_DIRECT        A row has exactly one entry: C row = scaled copy of one B row
 //                     (reference: directSpGEMM*, spECK_HashSpGEMM.cuh:543-589)
-//   BIN_SORT0 + c     products <= 4<<c (c = 0..7): register bitonic sort of the row's products by a
-//                     lane group; c = 8..22: by a CTA of 2..16 warps (512 keys per warp),
-//                     duplicates folded after the sort
-//                     (replaces the smem hash + O(n^2) rank sort, :591-866)
-//   BIN_DENSE         more products: CTA per row, sparse-cleared column bitmap in
-//                     shared memory, popcount ranks give the sorted position of every
-//                     product, values accumulate with fp RED into C
+//   BIN_SORT0 + c     c = 0..7: products <= 4<<c, one lane group per row, register bitonic sort (sort_rows.cuh);
+//                     c = 8..23: 513..16384 products, one CTA per row: two/three-level column bitmap ranks
+//                     (rank_cta.cuh); CTA bitonic sort (sort_cta.cuh) only as the fallback for matrices wider
+//                     than the rank kernels take.  Mapped rows: numeric = k_map_rows / k_map_rows_cta
+//                     (replaces the smem hash + O(n^2) rank sort / radix sort, :591-866, :1856-1925)
+//   BIN_DENSE(_LOCAL) banded rows and rows with more products: CTA per row, sparse-cleared column bitmap in
+//                     shared memory, popcount ranks give the sorted position of every product, values
+//                     accumulate in shared memory or with fp RED into C
 //                     (replaces denseSpGEMM{Count,Numeric}, :1300-1711)
 #pragma once
 #include <cstdint>
@@ -28,9 +30,9 @@ constexpr int NUM_CTA_SORT = 16;            // CTA classes: 1024, 1536, ..., 819
 constexpr int NUM_SORT = NUM_WARP_SORT + NUM_CTA_SORT;
 constexpr int BIN_DIRECT = 0;
 constexpr int BIN_SORT0 = 1;
-constexpr int BIN_DENSE_LOCAL = BIN_SORT0 + NUM_SORT;   // 24: bitmap path, column extent <= DENSE_LOCAL_COLS
-constexpr int BIN_DENSE = BIN_DENSE_LOCAL + 1;          // 25: bitmap path, wide rows
-constexpr int NUM_BINS = BIN_DENSE + 1;                 // 26
+constexpr int BIN_DENSE_LOCAL = BIN_SORT0 + NUM_SORT;   // 25: bitmap path, column extent <= DENSE_LOCAL_COLS
+constexpr int BIN_DENSE = BIN_DENSE_LOCAL + 1;          // 26: bitmap path, wide rows
+constexpr int NUM_BINS = BIN_DENSE + 1;                 // 27
 constexpr int DENSE_LOCAL_BITS = 14;
 constexpr u32 DENSE_LOCAL_COLS = (1u << DENSE_LOCAL_BITS) - 128u;  // window starts chunk-aligned below the row minimum
 constexpr u32 SORT_MAX_PRODUCTS = 8192;     // largest row of the CTA sort kernels (sort_cta.cuh)
