@@ -116,31 +116,47 @@ struct RankLayout {
 // popcount prefix of a level: words[0..n) (padded with zero words to a multiple of 4 by the caller)
 // -> pre[j] = number of set bits in words[0..j), returns the total.  Threads own consecutive groups of four
 // words (one 16-byte load, one 8-byte store of four packed u16 prefixes).
-template <int THREADS, bool WRITE_PREFIX>
+// Thread t owns the MAXG consecutive groups t * MAXG ..; MAXG is a compile-time bound (1024 top words / 4 / THREADS
+// or E / 4), so both loops are fully unrolled.
+template <int THREADS, int MAXG, bool WRITE_PREFIX>
 __device__ __forceinline__ u32 rank_scan_level(const u32 *bits, unsigned short *pre, u32 words, u32 *sWarp)
 {
-    const u32 tid = threadIdx.x;
     const u32 groups = (words + 3) >> 2;
-    const u32 per = (groups + THREADS - 1) / THREADS;
-    const u32 g0 = min(groups, tid * per), g1 = min(groups, g0 + per);
+    const u32 g0 = threadIdx.x * MAXG;
     u32 s = 0;
-#pragma unroll 1
-    for (u32 g = g0; g < g1; ++g) {
-        const uint4 v = reinterpret_cast<const uint4 *>(bits)[g];
-        s += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+        if (g0 + k < groups) {
+            const uint4 w = reinterpret_cast<const uint4 *>(bits)[g0 + k];
+            s += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+        }
     }
     u32 tot;
     u32 run = cta_exclusive_scan<THREADS>(s, sWarp, &tot);
-    if (WRITE_PREFIX) {
-#pragma unroll 1
-        for (u32 g = g0; g < g1; ++g) {
-            const uint4 v = reinterpret_cast<const uint4 *>(bits)[g];
-            const u32 p1 = run + __popc(v.x), p2 = p1 + __popc(v.y), p3 = p2 + __popc(v.z);
-            reinterpret_cast<uint2 *>(pre)[g] = make_uint2(run | (p1 << 16), p2 | (p3 << 16));
-            run = p3 + __popc(v.w);
+    if (WRITE_PREFIX) {   // the words are read again: keeping 4 * MAXG popcounts across the scan spills at 32 registers
+#pragma unroll
+        for (int k = 0; k < MAXG; ++k) {
+            if (g0 + k < groups) {
+                const uint4 w = reinterpret_cast<const uint4 *>(bits)[g0 + k];
+                const u32 p1 = run + __popc(w.x), p2 = p1 + __popc(w.y), p3 = p2 + __popc(w.z);
+                reinterpret_cast<uint2 *>(pre)[g0 + k] = make_uint2(run | (p1 << 16), p2 | (p3 << 16));
+                run = p3 + __popc(w.w);
+            }
         }
     }
     return tot;
+}
+
+// clears the first `words` words (rounded up to groups of four) of a level; same compile-time bound
+template <int THREADS, int MAXG>
+__device__ __forceinline__ void rank_clear_level(u32 *bits, u32 words)
+{
+    const u32 groups = (words + 3) >> 2;
+#pragma unroll
+    for (int k = 0; k < MAXG; ++k) {
+        const u32 g = threadIdx.x + k * THREADS;
+        if (g < groups) reinterpret_cast<uint4 *>(bits)[g] = make_uint4(0, 0, 0, 0);
+    }
 }
 
 // MODE: RANK_COUNT   symbolic, distinct columns per row only
@@ -163,6 +179,8 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     constexpr bool DESC = MODE == RANK_MAP;   // row parameters from the descriptor, B-row bounds from aSeg
     static_assert(LEVELS == 2 || (LEVELS == 3 && !NUMERIC), "three levels: symbolic modes only");
     constexpr int TOPSHIFT = 5 * LEVELS;      // column bits below a top word
+    constexpr int TOPG = (RANK_TOP_WORDS / 4 + THREADS - 1) / THREADS;   // groups of four words per thread: top level
+    constexpr int LEAFG = (E + 3) / 4;                                   // ... compact levels (<= CAP words)
     using L = RankLayout<THREADS, E, T, NUMERIC, LEVELS>;
     constexpr u32 NONE = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -202,8 +220,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         cBase = cRp[row];
         nnzRow = cRp[row + 1] - cBase;
     }
-#pragma unroll 1
-    for (u32 j = tid; j < (topWords + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(top)[j] = make_uint4(0, 0, 0, 0);
+    rank_clear_level<THREADS, TOPG>(top, topWords);
     __syncthreads();
 
     // ---------------------------------------------------------------- gather (flat over the CTA)
@@ -243,8 +260,9 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         __syncthreads();
         constexpr int GU = E < 4 ? E : 4;   // products per thread in flight
         const u32 first = max(myFirst, base), last = min(min(myFirst + EP, n), base + total);
+        const u32 mine = first < last ? last - first : 0u;   // this thread's products in the batch
         SegWalk<T, NUMERIC> walk;
-        if (first < last) walk.start(first - base, sTab, sIncl, sBs, sAv);
+        if (mine) walk.start(first - base, sTab, sIncl, sBs, sAv);
 #pragma unroll
         for (int i0 = 0; i0 < E; i0 += GU) {
             if ((u32)i0 >= EP) break;           // CTA-uniform
@@ -255,7 +273,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
                 const u32 gp = myFirst + (u32)(i0 + u);
                 q[u] = NONE;
                 av[u] = (T)0;
-                if (gp >= first && gp < last) {
+                if (gp - first < mine) {   // unsigned: also false for gp < first
                     q[u] = walk.locate(gp - base, sIncl, sBs, sAv);
                     if (NUMERIC) av[u] = walk.av;
                 }
@@ -283,9 +301,8 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     // 1024-column blocks: same step as the leaf level below, one digit higher
     u32 upperWords = topWords;   // words of the level above the leaves
     if (LEVELS == 3) {
-        const u32 mids = rank_scan_level<THREADS, true>(top, topPre, topWords, sWarp);
-#pragma unroll 1
-        for (u32 j = tid; j < (mids + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(mid)[j] = make_uint4(0, 0, 0, 0);
+        const u32 mids = rank_scan_level<THREADS, TOPG, true>(top, topPre, topWords, sWarp);
+        rank_clear_level<THREADS, LEAFG>(mid, mids);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < E; ++i) {
@@ -305,9 +322,9 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     unsigned short *upperPre = LEVELS == 3 ? midPre : topPre;
 
     // ---------------------------------------------------------------- leaf words of the touched chunks
-    const u32 leaves = rank_scan_level<THREADS, true>(upper, upperPre, upperWords, sWarp);
-#pragma unroll 1
-    for (u32 j = tid; j < (leaves + 3) >> 2; j += THREADS) reinterpret_cast<uint4 *>(leaf)[j] = make_uint4(0, 0, 0, 0);
+    const u32 leaves = LEVELS == 3 ? rank_scan_level<THREADS, LEAFG, true>(upper, upperPre, upperWords, sWarp)
+                                   : rank_scan_level<THREADS, TOPG, true>(upper, upperPre, upperWords, sWarp);
+    rank_clear_level<THREADS, LEAFG>(leaf, leaves);
     __syncthreads();
     u32 dup = 0;   // bit i: slot i is not the first product of its column
 #pragma unroll
@@ -327,11 +344,11 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
     __syncthreads();
 
     if (MODE == RANK_COUNT) {
-        const u32 distinct = rank_scan_level<THREADS, false>(leaf, nullptr, leaves, sWarp);
+        const u32 distinct = rank_scan_level<THREADS, LEAFG, false>(leaf, nullptr, leaves, sWarp);
         if (tid == 0) cRp[row] = distinct;
         return;
     } else if (MODE == RANK_MAP) {
-        const u32 distinct = rank_scan_level<THREADS, true>(leaf, leafPre, leaves, sWarp);
+        const u32 distinct = rank_scan_level<THREADS, LEAFG, true>(leaf, leafPre, leaves, sWarp);
         if (tid == 0) cRp[row] = distinct;
         __syncthreads();
         unsigned short *map = rankMap + mapOff;
@@ -346,7 +363,7 @@ k_rank_rows(const u32 *__restrict__ perm, const u32 *__restrict__ aRp, const u32
         }
         return;
     } else {
-        rank_scan_level<THREADS, true>(leaf, leafPre, leaves, sWarp);
+        rank_scan_level<THREADS, LEAFG, true>(leaf, leafPre, leaves, sWarp);
         __syncthreads();
         // ------------------------------------------------------------ first product of a column: plain stores
 #pragma unroll
@@ -467,8 +484,9 @@ k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
         __syncthreads();
         constexpr int GU = E < 4 ? E : 4;   // products per thread in flight
         const u32 first = max(myFirst, base), last = min(min(myFirst + EP, n), base + total);
+        const u32 mine = first < last ? last - first : 0u;   // this thread's products in the batch
         SegWalk<T, true> walk;
-        if (first < last) walk.start(first - base, sTab, sIncl, sBs, sAv);
+        if (mine) walk.start(first - base, sTab, sIncl, sBs, sAv);
 #pragma unroll
         for (int i0 = 0; i0 < E; i0 += GU) {
             if ((u32)i0 >= EP) break;           // CTA-uniform
@@ -480,7 +498,7 @@ k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
                 q[u] = NONE;
                 av[u] = (T)0;
                 code[u] = 0;
-                if (gp >= first && gp < last) {
+                if (gp - first < mine) {   // unsigned: also false for gp < first
                     code[u] = map[gp];
                     q[u] = walk.locate(gp - base, sIncl, sBs, sAv);
                     av[u] = walk.av;
