@@ -254,30 +254,35 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
         return;
     } else if (MODE == SORT_MAP) {
         // ------------------------------------------------------------ symbolic + rank map
+        // lane l holds the sorted elements l*E .. l*E+E-1: heads of equal-column runs are found in registers, a
+        // group scan of the per-lane head counts gives every element its position; the codes go to shared memory
+        // in product order (they are stored to the map coalesced below)
+        constexpr KeyT IDXMASK = ((KeyT)1 << IDXBITS) - 1;
+        const KeyT prevLast = __shfl_up_sync(gmask, reg[E - 1], 1, G);
+        u32 headBits = 0, cnt = 0;
 #pragma unroll
         for (int r = 0; r < E; ++r) {
-            const u32 idx = l * E + r;
-            keys[idx + (idx >> 5)] = reg[r];
+            const KeyT prev = (r == 0) ? prevLast : reg[r - 1];
+            const bool first = (r == 0) && (l == 0);
+            // element l*E + r is a product iff it lies below ops (sentinels sort last; a key may equal the sentinel)
+            const bool head = l * E + r < ops && (first || (u32)(reg[r] >> IDXBITS) != (u32)(prev >> IDXBITS));
+            headBits |= (head ? 1u : 0u) << r;
+            cnt += head ? 1u : 0u;
         }
-        __syncwarp(gmask);
-        constexpr KeyT IDXMASK = ((KeyT)1 << IDXBITS) - 1;
-        u32 running = 0;   // distinct columns before this batch of G sorted products
-        for (u32 i0 = 0; i0 < ops; i0 += G) {
-            const u32 i = i0 + l;
-            const bool valid = i < ops;
-            KeyT key = 0;
-            bool head = false;
-            if (valid) {
-                key = keys[i + (i >> 5)];
-                head = (i == 0) || ((u32)(keys[(i - 1) + ((i - 1) >> 5)] >> IDXBITS) != (u32)(key >> IDXBITS));
-            }
-            const u32 bal = __ballot_sync(gmask, head);
-            const u32 gb = (G == 32) ? bal : ((bal >> (laneW - l)) & ((1u << (G & 31)) - 1u));
-            if (valid) {   // position = heads at or before this product - 1
-                const u32 rank = running + __popc(gb & ((2u << l) - 1u)) - 1u;
-                codes[(u32)(key & IDXMASK)] = (unsigned short)(rank | (head ? 0u : MAP_DUP));
-            }
-            running += __popc(gb);
+        u32 incl = cnt;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const u32 t = __shfl_up_sync(gmask, incl, d, G);
+            if ((int)l >= d) incl += t;
+        }
+        const u32 running = __shfl_sync(gmask, incl, G - 1, G);   // distinct columns of the row
+        u32 pos = incl - cnt;                                      // heads in the lanes before this one
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const bool head = (headBits >> r) & 1u;
+            pos += head ? 1u : 0u;
+            if (l * E + r < ops)   // position = heads at or before this product - 1
+                codes[(u32)(reg[r] & IDXMASK)] = (unsigned short)((pos - 1u) | (head ? 0u : MAP_DUP));
         }
         __syncwarp(gmask);
         if (active) {
