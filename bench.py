@@ -210,7 +210,7 @@ def main():
     ap.add_argument("--workload", default="rmat20")
     ap.add_argument("--seed", type=int, default=20)
     ap.add_argument("--cpu-stride", type=int, default=1, help="row stride of the bounded CPU sample (1 = the whole workload)")
-    ap.add_argument("--cpu-reps", type=int, default=5, help="repetitions of the CPU sample in the GPU arm (about 10 s in total)")
+    ap.add_argument("--cpu-reps", type=int, default=10, help="repetitions of the CPU sample in the GPU arm (about 10-20 s in total)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true",
