@@ -31,6 +31,10 @@ def main():
             k["rd"] = to_gb(v, x["Metric Unit"])
         elif m == "dram__bytes_write.sum":
             k["wr"] = to_gb(v, x["Metric Unit"])
+        elif m == "smsp__inst_executed.sum":
+            k["inst"] = v
+        elif m == "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum":
+            k["wf"] = v
     rows = list(launches.values())
     idx = [i for i, x in enumerate(rows) if "k_analyze" in x["name"]]
     s = idx[which]
@@ -45,7 +49,7 @@ def main():
         short = (m.group(1) + (m.group(2) or "")) if m else x["name"][:60]
         if "k_scan<unsigned int>" in short:
             phase = "scan"
-        elif phase == "analysis" and ("k_rank_rows" in short or "k_sort_rows" in short or "k_dense_rows" in short):
+        elif phase == "analysis" and ("k_rank_rows" in short or "k_rank_flat" in short or "k_hash_count" in short or "k_sort_rows" in short or "k_dense_rows" in short):
             phase = "symbolic"
         elif phase == "scan" and "k_scan" not in short:
             phase = "numeric"
@@ -54,6 +58,8 @@ def main():
         a[1] += x.get("rd", 0.0)
         a[2] += x.get("wr", 0.0)
         dram = f"  dram rd {x['rd']:6.3f} wr {x['wr']:6.3f} GB" if "rd" in x else ""
+        if "inst" in x:
+            dram += f"  inst {x['inst'] / 1e6:8.1f} M  smem wf {x.get('wf', 0.0) / 1e6:8.1f} M"
         print(f"{x['ms']:9.3f} ms {x['ms'] / tot * 100:5.1f}%  grid={x['grid']:<14} block={x['block']:<13} {short[:58]:58s}{dram}")
     for ph, a in agg.items():
         print(f"# phase {ph:9s}: {a[0]:7.3f} ms  dram read {a[1]:7.3f} GB  write {a[2]:7.3f} GB")

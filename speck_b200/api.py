@@ -200,8 +200,15 @@ class Context:
 
     # ---- MultiplyspECK
     def multiply(self, A: DeviceCSR, B: DeviceCSR, C: DeviceCSR = None, timings=None) -> DeviceCSR:
+        if A.dtype != B.dtype:
+            raise SpeckError(f"A is {A.dtype} but B is {B.dtype}: both operands must have the same value type")
         if C is None:
             C = DeviceCSR(self, A.dtype)
+        elif C.dtype != A.dtype:
+            if C.s.data or C.s.nnz:
+                raise SpeckError(f"C holds {C.dtype} values but A and B are {A.dtype}: free C first (its value buffer "
+                                 "would be reused with the wrong element size)")
+            C.dtype = A.dtype
         fn = self.lib.speck_b200_spgemm_f32 if A.dtype == np.float32 else self.lib.speck_b200_spgemm_f64
         t = timings if timings is not None else TimingsStruct()
         _check(fn(self.h, ctypes.byref(A.s), ctypes.byref(B.s), ctypes.byref(C.s), ctypes.byref(t)))

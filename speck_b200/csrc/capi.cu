@@ -60,11 +60,12 @@ struct speck_ctx {
     cudaEvent_t evStage[6] = {};
     Scalars *dSc = nullptr;
     Scalars *hSc = nullptr;  // pinned
-    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore, mapLen, mapBase, rankMap, aSeg, desc, rowInfo;
+    DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore, mapLen, mapBase, rankMap, aSeg, aOff, desc, rowInfo;
     DevBuf stage[6];          // device staging of the *_host entry points (A: rp, ci, v; B: rp, ci, v)
     void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
     size_t hostOutCap[3] = {};
     speck_csr hostC = {};     // device C kept across *_host calls (reuse rules)
+    size_t hostCValBytes = 0; // element size of hostC.data (f32 and f64 host calls share the context)
     u32 sortMax = RANK_MAX_PRODUCTS;  // rows with more products take the bitmap path (clamped per multiply)
     bool rankPath = true;     // rows of 513..8192 products: rank classes instead of the CTA sort classes
     int symStreams = NSIDE;   // side streams used by the symbolic phase (instruction-bound kernels overlap well)
@@ -75,6 +76,11 @@ struct speck_ctx {
     size_t rankMapMaxBytes = ~(size_t)0;  // test hook: larger maps are treated as "does not fit" (exercises the fallbacks)
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
+    int segNum = 0;           // mapped numeric CTA classes: 1 = segment-major kernel (map_seg.cuh; measured slower: fewer
+                              // loads in flight per SM, profiles/r2_notes.md), 0 = k_map_rows_cta
+    int flatSym = 1;          // mapped two-level symbolic rank kernel: 1 = flat staged variant (rank_flat.cuh), 0 = rank_cta.cuh
+    int flatE = 8;            // ... product slots per thread of the flat variant (8 or 16)
+    bool hashCount = false;   // experiment: count-only symbolic by hashing when no rank map is recorded
     bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
     u32 launches = 0;
     speck_stats stats = {};
@@ -179,6 +185,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if ((rc = ensure(c->mapLen, (size_t)(rows + 1) * 4))) return rc;
         if ((rc = ensure(c->mapBase, (size_t)(rows + 1) * 8))) return rc;
         if ((rc = ensure(c->aSeg, (size_t)A->nnz * sizeof(uint2)))) return rc;
+        if (c->segNum && (rc = ensure(c->aOff, (size_t)A->nnz * sizeof(u32)))) return rc;
         if ((rc = ensure(c->desc, (size_t)rows * sizeof(RowDesc)))) return rc;
     }
     if ((rc = ensure(c->rowInfo, (size_t)B->rows * sizeof(uint4)))) return rc;
@@ -197,7 +204,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // ---- analysis + binning
     launch_row_info(lc, (u32)B->rows, bRp, bCi, (uint4 *)c->rowInfo.p);
     launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
-                   wantMap ? (uint2 *)c->aSeg.p : nullptr, (const uint4 *)c->rowInfo.p);
+                   wantMap ? (uint2 *)c->aSeg.p : nullptr, (const uint4 *)c->rowInfo.p,
+                   wantMap && c->segNum ? (u32 *)c->aOff.p : nullptr);
     launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (u32 *)c->mapLen.p : nullptr,
                        useRank, c->mapMinClass);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
@@ -272,8 +280,13 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
                                       rowMin, rowMax, nullptr, cRp);
                 continue;
             }
-            launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp,
-                                 desc ? desc + binStart[b0] : nullptr, aSeg, rankMap, rankLevels);
+            if (rankMap && rankLevels == 2 && c->flatSym)
+                launch_rank_flat(ls, 1024u << g, c->flatE, desc + binStart[b0], cnt, aSeg, bCi, rankMap, cRp);
+            else if (!rankMap && c->hashCount && g < RANK_GROUPS - 1)
+                launch_hash_count(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, cRp);
+            else
+                launch_rank_symbolic(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp,
+                                     desc ? desc + binStart[b0] : nullptr, aSeg, rankMap, rankLevels);
         }
     }
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
@@ -291,6 +304,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
                                  rowOps, cRp, mapped ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
     }
     join_streams(c);
+    CU_TRY(cudaGetLastError());   // launch / attribute errors of the symbolic kernels (side streams are joined)
     cudaEventRecord(c->evStage[2], c->main);
 
     // ---- scan + nnz read-back
@@ -346,7 +360,9 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
                                         bV, colsB, rowMin, rowMax, nullptr, cRp, cCi, cV);
                 continue;
             }
-            if (rankMap)
+            if (rankMap && c->segNum)
+                launch_map_seg<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, (const u32 *)c->aOff.p, aV, bCi, bV, rankMap, cCi, cV);
+            else if (rankMap)
                 launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
             else if (rankLevels == 2)
                 launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
@@ -394,7 +410,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
     cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
     st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->rowMin.cap + c->rowMax.cap + c->tileState.cap + c->bitmapStore.cap +
-                         c->mapLen.cap + c->mapBase.cap + c->rankMap.cap + c->aSeg.cap + c->desc.cap + c->rowInfo.cap;
+                         c->mapLen.cap + c->mapBase.cap + c->rankMap.cap + c->aSeg.cap + c->aOff.cap + c->desc.cap + c->rowInfo.cap;
     if (tm) {
         float allocMs = 0.f;
         cudaEventElapsedTime(&allocMs, c->evStage[3], c->evStage[4]);
@@ -456,13 +472,26 @@ int spgemm_host_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck
         dst[m]->data = c->stage[m * 3 + 2].p;
     }
     if (alias) { dB = dA; dB.rows = B->rows; dB.cols = B->cols; }
+    if (c->hostCValBytes != sizeof(T) && c->hostC.data) {   // the kept value buffer was sized for the other type
+        cudaFree(c->hostC.data);
+        c->hostC.data = nullptr;
+        c->hostC.nnz = 0;
+    }
+    c->hostCValBytes = sizeof(T);
     int rc = spgemm_impl<T>(c, &dA, &dB, &c->hostC, nullptr);
     if (rc) return rc;
     const speck_csr &dC = c->hostC;
     uint64_t down = 0;
     C->rows = A->rows; C->cols = B->cols; C->nnz = dC.nnz;
     C->row_offsets = nullptr; C->col_ids = nullptr; C->data = nullptr;
-    if (dC.row_offsets) {
+    if (dC.nnz == 0) {
+        // empty product (A.nnz == 0, B.nnz == 0 or P == 0): the device conventions of the reference leave
+        // row_offsets stale or null (Multiply.cu:67-70, 256-261); the host entry returns a well-formed empty CSR
+        const size_t bytes = (A->rows + 1) * 4;
+        if ((rc = ensure_host(c, 0, bytes))) return rc;
+        memset(c->hostOut[0], 0, bytes);
+        C->row_offsets = (u32 *)c->hostOut[0];
+    } else if (dC.row_offsets) {
         const size_t bytes[3] = {(dC.rows + 1) * 4, dC.nnz * 4, dC.nnz * sizeof(T)};
         const void *dp[3] = {dC.row_offsets, dC.col_ids, dC.data};
         for (int j = 0; j < 3; ++j) {
@@ -507,6 +536,8 @@ extern "C" {
 int speck_b200_abi_version(void) { return SPECK_B200_ABI_VERSION; }
 const char *speck_b200_last_error(void) { return g_err; }
 
+int speck_b200_destroy(speck_ctx *c);
+
 int speck_b200_create(int device, speck_ctx **out)
 {
     if (!out) return fail(SPECK_ERR_INVALID, "null out pointer");
@@ -526,15 +557,28 @@ int speck_b200_create(int device, speck_ctx **out)
     if (!c) return fail(SPECK_ERR_OOM, "host allocation failed");
     c->device = device;
     c->smCount = prop.multiProcessorCount;
-    CU_TRY(cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking));
-    for (int i = 0; i < NSIDE; ++i) {
-        CU_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
-        CU_TRY(cudaEventCreateWithFlags(&c->evJoin[i], cudaEventDisableTiming));
+    // The main stream is a blocking stream: uploads made by the host layer with plain cudaMemcpy / cudaMemset on
+    // the legacy default stream (host/dCSR.cpp) are ordered before the multiply without an explicit
+    // synchronisation.  The side streams only ever run between a fork from and a join into the main stream.
+    const int rc = [&]() -> int {
+        CU_TRY(cudaStreamCreate(&c->main));
+        for (int i = 0; i < NSIDE; ++i) {
+            CU_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&c->evJoin[i], cudaEventDisableTiming));
+        }
+        CU_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        for (auto &e : c->evStage) CU_TRY(cudaEventCreate(&e));
+        CU_TRY(cudaMalloc(&c->dSc, sizeof(Scalars)));
+        CU_TRY(cudaMallocHost(&c->hSc, sizeof(Scalars)));
+        return SPECK_OK;
+    }();
+    if (rc != SPECK_OK) {   // do not leak the partially built context
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        speck_b200_destroy(c);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
     }
-    CU_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
-    for (auto &e : c->evStage) CU_TRY(cudaEventCreate(&e));
-    CU_TRY(cudaMalloc(&c->dSc, sizeof(Scalars)));
-    CU_TRY(cudaMallocHost(&c->hSc, sizeof(Scalars)));
     *out = c;
     return SPECK_OK;
 }
@@ -544,7 +588,7 @@ int speck_b200_destroy(speck_ctx *c)
     if (!c) return SPECK_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc); release(c->rowInfo);
+    release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->aOff); release(c->desc); release(c->rowInfo);
     for (auto &b : c->stage) release(b);
     for (auto &h : c->hostOut) if (h) cudaFreeHost(h);
     if (c->hostC.data) cudaFree(c->hostC.data);
@@ -712,6 +756,23 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         c->rankMapOn = value != 0;
         return SPECK_OK;
     }
+    if (!strcmp(key, "seg_num")) {
+        c->segNum = value != 0;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "flat_sym")) {
+        c->flatSym = value != 0;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "flat_e")) {
+        if (value != 8 && value != 16) return fail(SPECK_ERR_INVALID, "flat_e must be 8 or 16");
+        c->flatE = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "hash_count")) {
+        c->hashCount = value != 0;
+        return SPECK_OK;
+    }
     if (!strcmp(key, "rank_path")) {
         c->rankPath = value != 0;
         return SPECK_OK;
@@ -719,7 +780,7 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "release_workspace")) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->desc); release(c->rowInfo);
+        release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->aOff); release(c->desc); release(c->rowInfo);
         for (auto &b : c->stage) release(b);
         return SPECK_OK;
     }

@@ -92,11 +92,13 @@ struct LaunchCtx {
     u32 *launches;   // incremented per kernel launch
 };
 
+// aOff (optional, nnz(A) entries): index of every A entry's first product in its row's flat product enumeration
+// (exclusive prefix of the B-row lengths inside the row), so that the segment-major numeric kernel needs no scan.
 // aSeg (optional, nnz(A) entries): (begin, end) of the B row referenced by every A entry, so that the row
 // kernels need one load level (aSeg) instead of two (A.col_ids -> B.row_offsets)
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg, const uint4 *rowInfo);
+                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff = nullptr);
 // rowInfo[k] = (begin, end, first column, last column) of B row k: one gather per A entry in the analysis
 void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *bCi, uint4 *rowInfo);
 // descriptors of perm[0..count): symbolic flavour (c0/c1 = column extent), then switched to the numeric
@@ -151,6 +153,18 @@ void launch_rank_symbolic(const LaunchCtx &lc, u32 capProducts, const u32 *perm,
                           const u32 *aCi, const u32 *bRp, const u32 *bCi, const u32 *rowOps, const u32 *rowMin,
                           const u32 *rowMax, u32 *rowNnz, const RowDesc *desc, const uint2 *aSeg,
                           unsigned short *rankMap, int levels /* 2: cols(B) <= 2^20, 3: <= 2^25 */);
+// flat (staged) variant of the mapped two-level symbolic kernel (rank_flat.cuh); perThread = product slots per
+// thread (8 or 16)
+void launch_rank_flat(const LaunchCtx &lc, u32 capProducts, int perThread, const RowDesc *desc, u32 count,
+                      const uint2 *aSeg, const u32 *bCi, unsigned short *rankMap, u32 *cRp);
+// segment-major numeric kernel of the mapped CTA classes (map_seg.cuh); aOff from launch_analyze
+template <typename T>
+void launch_map_seg(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
+                    const u32 *aOff, const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap,
+                    u32 *cCi, T *cV);
+// count-only symbolic by shared-memory hashing (experiment)
+void launch_hash_count(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
+                       const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 *cRp);
 template <typename T>
 void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, u32 count, const u32 *aRp,
                          const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                                                  u32 *__restrict__ rowOps, u32 *__restrict__ rowMin,
                                                  u32 *__restrict__ rowMax, u32 *__restrict__ rowNnz, Scalars *sc,
                                                  u32 sortMax, uint2 *__restrict__ aSeg,
-                                                 const uint4 *__restrict__ rowInfo)
+                                                 const uint4 *__restrict__ rowInfo, u32 *__restrict__ aOff)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -59,12 +59,15 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
     u32 cmin = 0xffffffffu, cmax = 0u;  // column extent of the row's products: B rows are sorted, so the
                                         // first / last entry of each referenced B row bound it (the
                                         // reference's rowColMinMax, common.cuh:395-400)
-    if (row < rows) {
-        const u32 beg = aRp[row], end = aRp[row + 1];
-        aLen = end - beg;
-        for (u32 p = beg + lane; p < end; p += LA) {
+    const u32 beg = row < rows ? aRp[row] : 0u, end = row < rows ? aRp[row + 1] : 0u;
+    aLen = end - beg;
+    // all LA lanes of the group run the same number of iterations (the per-entry product offsets need a group scan)
+    const u32 gmask = LA == 32 ? 0xffffffffu : (((1u << (LA & 31)) - 1u) << ((threadIdx.x & 31) - lane));
+    for (u32 p0 = beg; p0 < end; p0 += LA) {
+        const u32 p = p0 + lane;
+        u32 len = 0, bs = 0, be = 0;
+        if (p < end) {
             const u32 k = __ldg(aCi + p);
-            u32 bs, be;
             if (rowInfo) {
                 const uint4 ri = __ldg(rowInfo + k);
                 bs = ri.x; be = ri.y;
@@ -77,13 +80,25 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                     cmax = max(cmax, __ldg(bCi + be - 1));
                 }
             }
-            ops64 += (u64)(be - bs);
-            if (aSeg) aSeg[p] = make_uint2(bs, be);
+            len = be - bs;
         }
+        if (aOff) {   // index of the entry's first product in the row's flat enumeration (u32: rows beyond 2^32 products are not mapped)
+            u32 incl = len;
+#pragma unroll
+            for (int d = 1; d < LA; d <<= 1) {
+                const u32 t = __shfl_up_sync(gmask, incl, d, LA);
+                if ((int)lane >= d) incl += t;
+            }
+            if (p < end) aOff[p] = (u32)ops64 + incl - len;
+            ops64 += (u64)__shfl_sync(gmask, incl, LA - 1, LA);   // every lane carries the running row total
+        } else {
+            ops64 += (u64)len;
+        }
+        if (aSeg && p < end) aSeg[p] = make_uint2(bs, be);
     }
 #pragma unroll
     for (int d = LA / 2; d >= 1; d >>= 1) {
-        ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
+        if (!aOff) ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
         cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, d));
         cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
     }
@@ -125,20 +140,20 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg, const uint4 *rowInfo)
+                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
     const int threads = 256;
     if (avg <= 3.0) {
         const u32 grid = (u32)(((u64)rows * 2 + threads - 1) / threads);
-        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo);
+        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff);
     } else if (avg <= 24.0) {
         const u32 grid = (u32)(((u64)rows * 8 + threads - 1) / threads);
-        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo);
+        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff);
     } else {
         const u32 grid = (u32)(((u64)rows * 32 + threads - 1) / threads);
-        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo);
+        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff);
     }
     ++*lc.launches;
 }

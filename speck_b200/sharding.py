@@ -22,11 +22,12 @@ def broadcast_csr(B, src=0, device="cpu"):
     tensors (rows, cols, nnz, rp, ci, v) for CUDA devices."""
     rank = dist.get_rank()
     dev = torch.device(device)
-    meta = torch.zeros(3, dtype=torch.int64, device=dev)
-    if rank == src:
-        meta = torch.tensor([B.rows, B.cols, B.nnz], dtype=torch.int64, device=dev)
+    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    if rank == src:   # the value type travels with the sizes: fp32 and fp64 are both instantiated
+        meta = torch.tensor([B.rows, B.cols, B.nnz, np.dtype(B.data.dtype).itemsize], dtype=torch.int64, device=dev)
     dist.broadcast(meta, src)
-    rows, cols, nnz = (int(x) for x in meta.tolist())
+    rows, cols, nnz, itemsize = (int(x) for x in meta.tolist())
+    vdtype = torch.float32 if itemsize == 4 else torch.float64
     if rank == src:
         rp = torch.from_numpy(np.ascontiguousarray(B.row_offsets).view(np.int32)).to(dev)
         ci = torch.from_numpy(np.ascontiguousarray(B.col_ids).view(np.int32)).to(dev)
@@ -34,7 +35,7 @@ def broadcast_csr(B, src=0, device="cpu"):
     else:
         rp = torch.empty(rows + 1, dtype=torch.int32, device=dev)
         ci = torch.empty(nnz, dtype=torch.int32, device=dev)
-        v = torch.empty(nnz, dtype=torch.float64, device=dev)
+        v = torch.empty(nnz, dtype=vdtype, device=dev)
     for t in (rp, ci, v):
         dist.broadcast(t, src)
     if dev.type == "cpu":

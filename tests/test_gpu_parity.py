@@ -26,19 +26,29 @@ def test_uniform_random(ctx, n, d, seed):
     check_case(ctx, M.uniform_random(n, n, d, seed), what=f"uniform {n} {d}")
 
 
-@pytest.fixture(params=[(16384, 1, 1), (8192, 1, 0), (8192, 0, 1), (8192, 0, 0), (1024, 1, 1), (64, 1, 1), (64, 1, 0)],
-                ids=["16384-rank-map", "8192-rank", "8192-sort-map", "8192-sort", "1024-map", "64-map", "64"])
+@pytest.fixture(params=[(16384, 1, 1, 1, 8, 0), (16384, 1, 1, 1, 16, 1), (16384, 1, 1, 0, 8, 0), (8192, 1, 0, 1, 8, 0),
+                        (8192, 0, 1, 1, 8, 0), (8192, 0, 0, 1, 8, 0), (1024, 1, 1, 1, 8, 1), (64, 1, 1, 1, 8, 0),
+                        (64, 1, 0, 1, 8, 0)],
+                ids=["16384-flat8-map", "16384-flat16-seg-map", "16384-rank-map", "8192-rank", "8192-sort-map", "8192-sort",
+                     "1024-seg-map", "64-map", "64"])
 def sort_max(ctx, request):
-    """Run a case with the sort/bitmap switch at several places, with the rank classes on and off and with
-    and without the symbolic->numeric rank map, so that every kernel family (lane-group sort, rank, CTA
-    sort, bitmap, mapped numeric) sees the same inputs."""
+    """Run a case with the sort/bitmap switch at several places, with the rank classes on and off, with
+    and without the symbolic->numeric rank map, and with the flat (staged) and the register-slot variant of
+    the mapped symbolic rank kernel, with the segment-major and the thread-blocked mapped numeric kernel, so that every kernel family (lane-group sort, rank, flat rank, CTA sort,
+    bitmap, mapped numeric) sees the same inputs."""
     ctx.set_option("sort_max", request.param[0])
     ctx.set_option("rank_path", request.param[1])
     ctx.set_option("rank_map", request.param[2])
+    ctx.set_option("flat_sym", request.param[3])
+    ctx.set_option("flat_e", request.param[4])
+    ctx.set_option("seg_num", request.param[5])
     yield request.param[0]
     ctx.set_option("sort_max", 16384)
     ctx.set_option("rank_path", 1)
     ctx.set_option("rank_map", 1)
+    ctx.set_option("flat_sym", 1)
+    ctx.set_option("flat_e", 8)
+    ctx.set_option("seg_num", 0)
 
 
 @pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16), (15, 16)])
