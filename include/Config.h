@@ -1,6 +1,7 @@
 // include/Config.h -- key/value run configuration read from an INI file (reference
 // include/Config.h + source/Config.cpp over inih).  Only the six keys the reference driver ever
-// reads are kept, plus `Device` for selecting the GPU.
+// reads are kept, plus `Device` for selecting the GPU and `Devices` (comma-separated list,
+// e.g. Devices=0,1,2,3) for the row-sharded multi-GPU run.
 #pragma once
 #include <map>
 #include <string>
@@ -8,7 +9,7 @@
 class Config {
 public:
     enum Key { InputFile, IterationsWarmUp, IterationsExecution, TrackIndividualTimes, TrackCompleteTimes,
-               CompareResult, Device };
+               CompareResult, Device, Devices };
 
     static void init(std::string path);   // parse `path` (section-less key=value, ';'/'#' comments)
     static void init();                   // no file: every get* returns its fallback

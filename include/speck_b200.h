@@ -122,6 +122,33 @@ int speck_b200_compare_f64(speck_ctx *ctx, const speck_csr *ref, const speck_csr
 int speck_b200_compare_f32(speck_ctx *ctx, const speck_csr *ref, const speck_csr *cmp,
                            int compare_data, double rel_tol);
 
+/* The same comparison with a report of the FIRST difference (smallest row, then kind, then position), which the
+ * reference's d_compare cannot give (it only raises a flag, Compare.cu:27-58).  Returns 1 / 0 / <0 like above. */
+typedef struct speck_mismatch {
+    uint64_t row;            /* first row that differs                                                  */
+    uint32_t kind;           /* 0 = row length, 1 = column id, 2 = value, 3 = shape / nnz of the matrices */
+    uint32_t index_in_row;   /* position inside the row (kinds 1 and 2)                                  */
+    uint32_t ref_len, cmp_len;
+    uint32_t ref_col, cmp_col;
+    double ref_val, cmp_val; /* values at that position (kind 2; 0 when a value array is missing)        */
+} speck_mismatch;
+int speck_b200_compare_report_f64(speck_ctx *ctx, const speck_csr *ref, const speck_csr *cmp, int compare_data,
+                                  double rel_tol, speck_mismatch *first);
+int speck_b200_compare_report_f32(speck_ctx *ctx, const speck_csr *ref, const speck_csr *cmp, int compare_data,
+                                  double rel_tol, speck_mismatch *first);
+
+/* GPU-side COO -> CSR for the loader path (replaces the host conversion, reference source/CSR.cpp:173-212): the
+ * (row, column) pairs are sorted on the device, stable; duplicate_policy SPECK_COO_KEEP keeps repeated (row, column)
+ * entries next to each other in input order (what the reference's loader does), SPECK_COO_SUM folds them into one
+ * entry (the duplicate-free form the multiply requires).  Inputs are device arrays of nnz entries; `out` receives
+ * cudaMalloc'ed arrays (free with speck_b200_free_csr).  Returns a speck_status (no message is recorded). */
+#define SPECK_COO_KEEP 0
+#define SPECK_COO_SUM 1
+int speck_b200_coo_to_csr_f64(speck_ctx *ctx, size_t rows, size_t cols, size_t nnz, const uint32_t *d_row_ids,
+                              const uint32_t *d_col_ids, const double *d_values, int duplicate_policy, speck_csr *out);
+int speck_b200_coo_to_csr_f32(speck_ctx *ctx, size_t rows, size_t cols, size_t nnz, const uint32_t *d_row_ids,
+                              const uint32_t *d_col_ids, const float *d_values, int duplicate_policy, speck_csr *out);
+
 /* Plumbing for bindings without a CUDA runtime of their own (ctypes / cgo / JNI). */
 int speck_b200_malloc(speck_ctx *ctx, void **dptr, size_t bytes);
 int speck_b200_free(speck_ctx *ctx, void *dptr);
@@ -131,6 +158,50 @@ int speck_b200_free_csr(speck_ctx *ctx, speck_csr *C); /* cudaFree the three arr
 int speck_b200_synchronize(speck_ctx *ctx);
 /* The context's main stream as a cudaStream_t (void* to keep this header CUDA-free). */
 void *speck_b200_stream(speck_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU (the reference is single-device, source/Executor.cpp:25 hard-codes device 0).
+ * Rows of C depend only on the matching rows of A and on all of B: A is cut into contiguous row slabs balanced by
+ * intermediate products, B is replicated once at setup (uploaded to the first device, copied to its peers over
+ * NVLink), every device multiplies its slab -- no exchange in the per-multiply path -- and the slabs of C are
+ * optionally concatenated on the first device (peer copies + a row_offsets fix-up).
+ * ------------------------------------------------------------------------------------------ */
+#define SPECK_MAX_SHARDS 16
+
+/* Row cuts of A balanced by products, computed on the device: analysis (row products) -> 64-bit scan -> search.
+ * cuts: host array of parts + 1 row indices (cuts[0] = 0, cuts[parts] = A->rows); part_products (may be NULL):
+ * host array of parts product counts.  A and B are device views on ctx's device. */
+int speck_b200_partition_rows(speck_ctx *ctx, const speck_csr *A, const speck_csr *B, int parts, uint32_t *cuts,
+                              uint64_t *part_products);
+
+typedef struct speck_shard_info {
+    int shards;
+    int concatenated;
+    uint32_t cuts[SPECK_MAX_SHARDS + 1];
+    uint64_t products[SPECK_MAX_SHARDS];
+    uint64_t nnz_c[SPECK_MAX_SHARDS];
+    float ms_device[SPECK_MAX_SHARDS];   /* CUDA-event ms of each slab's multiply on its device            */
+    float ms_setup;                      /* uploads, peer broadcast of B, partition (host wall clock)      */
+    float ms_multiply;                   /* host wall clock around the concurrent slab multiplies          */
+    float ms_concat;                     /* peer copies + offset fix-up into one CSR on the first device   */
+} speck_shard_info;
+
+typedef struct speck_shard_plan speck_shard_plan;
+
+/* Setup: HOST CSR A and B -> slabs of A on ctxs[0..n), B on every device.  One context per device. */
+int speck_b200_sharded_create_f64(speck_ctx **ctxs, int n, const speck_csr *A_host, const speck_csr *B_host,
+                                  speck_shard_plan **plan);
+int speck_b200_sharded_create_f32(speck_ctx **ctxs, int n, const speck_csr *A_host, const speck_csr *B_host,
+                                  speck_shard_plan **plan);
+/* One multiply: every device multiplies its slab concurrently (one host thread per device); the slabs of C stay
+ * on their devices and are reused by the next call (the reference's C-reuse rule per slab). */
+int speck_b200_sharded_multiply(speck_shard_plan *plan, speck_shard_info *info);
+/* Concatenate the slabs of the last multiply into one device CSR on ctxs[0] (C in/out, same ownership rules as
+ * speck_b200_spgemm_*).  SPECK_ERR_OVERFLOW when the total nnz does not fit u32 row_offsets: keep C distributed. */
+int speck_b200_sharded_concat(speck_shard_plan *plan, speck_csr *C, speck_shard_info *info);
+/* Borrowed views of slab g (device pointers on ctxs[g]'s device): its rows of A and of the last C. */
+int speck_b200_sharded_slab(speck_shard_plan *plan, int g, speck_csr *A_slab, speck_csr *C_slab);
+int speck_b200_sharded_destroy(speck_shard_plan *plan);
 
 /* Tuning knobs (integers; the defaults are the measured best, the switches exist so that the
  * tests can drive every kernel family over the same inputs):

@@ -19,16 +19,18 @@ SRCS="source/GPU/Multiply.cu source/GPU/Compare.cu source/GPU/memory.cpp source/
 build_variant() {  # name, extra include dir (may be empty)
     local name=$1 extra=$2 obj="$OUT/obj_$1"
     local so="$OUT/libspeck_ref_$name.so"
-    if [ -f "$so" ] && [ "$so" -nt "$HERE/ref_wrapper.cu" ] && [ "$so" -nt "$HERE/build_ref.sh" ]; then
+    if [ -f "$so" ] && [ "$so" -nt "$HERE/ref_wrapper.cu" ]; then
         echo "build_ref: $so up to date"; return
     fi
     local inc="-I$REF/include -I$REF/externals"
     [ -n "$extra" ] && inc="-I$extra $inc"
     local pids=""
-    for s in $SRCS; do
+    for s in $SRCS; do   # the reference's objects are rebuilt only when missing (its sources are read-only)
         o="$obj/$(basename ${s%.*}).o"
-        nvcc $FLAGS $inc -x cu -c "$REF/$s" -o "$o" &
-        pids="$pids $!"
+        if [ ! -f "$o" ]; then
+            nvcc $FLAGS $inc -x cu -c "$REF/$s" -o "$o" &
+            pids="$pids $!"
+        fi
     done
     nvcc $FLAGS $inc -c "$HERE/ref_wrapper.cu" -o "$obj/ref_wrapper.o" &
     pids="$pids $!"

@@ -53,6 +53,22 @@ class StatsStruct(ctypes.Structure):
                 ("ms_total", ctypes.c_float), ("workspace_bytes", ctypes.c_uint64)]
 
 
+MAX_SHARDS = 16
+
+
+class ShardInfoStruct(ctypes.Structure):
+    _fields_ = [("shards", ctypes.c_int), ("concatenated", ctypes.c_int),
+                ("cuts", ctypes.c_uint32 * (MAX_SHARDS + 1)), ("products", ctypes.c_uint64 * MAX_SHARDS),
+                ("nnz_c", ctypes.c_uint64 * MAX_SHARDS), ("ms_device", ctypes.c_float * MAX_SHARDS),
+                ("ms_setup", ctypes.c_float), ("ms_multiply", ctypes.c_float), ("ms_concat", ctypes.c_float)]
+
+
+class MismatchStruct(ctypes.Structure):
+    _fields_ = [("row", ctypes.c_uint64), ("kind", ctypes.c_uint32), ("index_in_row", ctypes.c_uint32),
+                ("ref_len", ctypes.c_uint32), ("cmp_len", ctypes.c_uint32), ("ref_col", ctypes.c_uint32),
+                ("cmp_col", ctypes.c_uint32), ("ref_val", ctypes.c_double), ("cmp_val", ctypes.c_double)]
+
+
 EXPORTS = [
     "speck_b200_abi_version", "speck_b200_last_error", "speck_b200_create", "speck_b200_destroy",
     "speck_b200_sm_count", "speck_b200_spgemm_f64", "speck_b200_spgemm_f32",
@@ -60,6 +76,10 @@ EXPORTS = [
     "speck_b200_row_products", "speck_b200_compare_f64", "speck_b200_compare_f32",
     "speck_b200_malloc", "speck_b200_free", "speck_b200_memcpy_h2d", "speck_b200_memcpy_d2h",
     "speck_b200_free_csr", "speck_b200_synchronize", "speck_b200_stream", "speck_b200_set_option",
+    "speck_b200_compare_report_f64", "speck_b200_compare_report_f32", "speck_b200_partition_rows",
+    "speck_b200_coo_to_csr_f64", "speck_b200_coo_to_csr_f32", "speck_b200_sharded_create_f64", "speck_b200_sharded_create_f32",
+    "speck_b200_sharded_multiply", "speck_b200_sharded_concat", "speck_b200_sharded_slab",
+    "speck_b200_sharded_destroy",
 ]
 
 _lib = None
@@ -90,6 +110,10 @@ def load_library():
                                             P(ctypes.c_uint64), P(ctypes.c_uint32)]
     for n in ("speck_b200_compare_f64", "speck_b200_compare_f32"):
         getattr(lib, n).argtypes = [vp, P(CsrStruct), P(CsrStruct), ctypes.c_int, ctypes.c_double]
+    for n in ("speck_b200_compare_report_f64", "speck_b200_compare_report_f32"):
+        getattr(lib, n).argtypes = [vp, P(CsrStruct), P(CsrStruct), ctypes.c_int, ctypes.c_double, P(MismatchStruct)]
+    for n in ("speck_b200_coo_to_csr_f64", "speck_b200_coo_to_csr_f32"):
+        getattr(lib, n).argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp, ctypes.c_int, P(CsrStruct)]
     lib.speck_b200_malloc.argtypes = [vp, P(vp), ctypes.c_size_t]
     lib.speck_b200_free.argtypes = [vp, vp]
     lib.speck_b200_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
@@ -99,6 +123,14 @@ def load_library():
     lib.speck_b200_stream.argtypes = [vp]
     lib.speck_b200_stream.restype = vp
     lib.speck_b200_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_longlong]
+    lib.speck_b200_partition_rows.argtypes = [vp, P(CsrStruct), P(CsrStruct), ctypes.c_int, P(ctypes.c_uint32),
+                                              P(ctypes.c_uint64)]
+    for n in ("speck_b200_sharded_create_f64", "speck_b200_sharded_create_f32"):
+        getattr(lib, n).argtypes = [P(vp), ctypes.c_int, P(CsrStruct), P(CsrStruct), P(vp)]
+    lib.speck_b200_sharded_multiply.argtypes = [vp, P(ShardInfoStruct)]
+    lib.speck_b200_sharded_concat.argtypes = [vp, P(CsrStruct), P(ShardInfoStruct)]
+    lib.speck_b200_sharded_slab.argtypes = [vp, ctypes.c_int, P(CsrStruct), P(CsrStruct)]
+    lib.speck_b200_sharded_destroy.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -270,12 +302,100 @@ class Context:
             self.lib.speck_b200_free(self.h, d)
         return out, int(P.value), int(mx.value)
 
+    def partition_rows(self, A: DeviceCSR, B: DeviceCSR, parts):
+        """-> (cuts uint32[parts+1], products uint64[parts]): contiguous row cuts of A balanced by products,
+        computed on the device (analysis -> 64-bit scan -> search)."""
+        cuts = (ctypes.c_uint32 * (parts + 1))()
+        prods = (ctypes.c_uint64 * parts)()
+        _check(self.lib.speck_b200_partition_rows(self.h, ctypes.byref(A.s), ctypes.byref(B.s), int(parts), cuts, prods))
+        return np.array(cuts[:], np.uint32), np.array(prods[:], np.uint64)
+
     def compare(self, ref: DeviceCSR, cmp: DeviceCSR, compare_data=False, rel_tol=1e-6):
         fn = self.lib.speck_b200_compare_f32 if ref.dtype == np.float32 else self.lib.speck_b200_compare_f64
         return bool(_check(fn(self.h, ctypes.byref(ref.s), ctypes.byref(cmp.s), int(compare_data), float(rel_tol))))
 
+    def coo_to_csr(self, rows, cols, row_ids, col_ids, values, sum_duplicates=False) -> DeviceCSR:
+        """GPU-side COO -> CSR of host COO arrays (uploaded here; the conversion itself runs on the device)."""
+        r = np.ascontiguousarray(row_ids, np.uint32)
+        c = np.ascontiguousarray(col_ids, np.uint32)
+        v = np.ascontiguousarray(values)
+        if v.dtype not in (np.float32, np.float64):
+            v = v.astype(np.float64)
+        n = r.size
+        bufs = [self._alloc(max(a.nbytes, 4)) for a in (r, c, v)]
+        try:
+            for b, a in zip(bufs, (r, c, v)):
+                if a.nbytes:
+                    _check(self.lib.speck_b200_memcpy_h2d(self.h, b, a.ctypes.data, a.nbytes))
+            d = DeviceCSR(self, v.dtype)
+            fn = self.lib.speck_b200_coo_to_csr_f32 if v.dtype == np.float32 else self.lib.speck_b200_coo_to_csr_f64
+            rc = fn(self.h, int(rows), int(cols), int(n), bufs[0], bufs[1], bufs[2], 1 if sum_duplicates else 0, ctypes.byref(d.s))
+            if rc < 0:
+                raise SpeckError(f"speck_b200_coo_to_csr failed with status {rc}")
+        finally:
+            for b in bufs:
+                self.lib.speck_b200_free(self.h, b)
+        return d
+
+    def compare_report(self, ref: DeviceCSR, cmp: DeviceCSR, compare_data=False, rel_tol=1e-6):
+        """-> (equal, first difference or None); kinds: 0 row length, 1 column id, 2 value, 3 shape / nnz."""
+        fn = self.lib.speck_b200_compare_report_f32 if ref.dtype == np.float32 else self.lib.speck_b200_compare_report_f64
+        m = MismatchStruct()
+        eq = bool(_check(fn(self.h, ctypes.byref(ref.s), ctypes.byref(cmp.s), int(compare_data), float(rel_tol), ctypes.byref(m))))
+        return eq, (None if eq else {f: getattr(m, f) for f, _ in MismatchStruct._fields_})
+
     def synchronize(self):
         _check(self.lib.speck_b200_synchronize(self.h))
+
+
+class ShardPlan:
+    """Row-sharded multiply over several devices of one box driven from one process (include/speck_b200.h:
+    speck_b200_sharded_*): HOST A and B in, product-balanced slabs of A on the contexts' devices, B replicated
+    over NVLink peer copies, concurrent slab multiplies, optional concatenation on the first device."""
+
+    def __init__(self, ctxs, A: HostCSR, B: HostCSR = None):
+        self.ctxs = list(ctxs)
+        self.lib = self.ctxs[0].lib
+        self.dtype = np.dtype(A.data.dtype)
+        B = A if B is None else B
+        self._keep = (A, B)
+
+        def st(m):
+            return CsrStruct(m.rows, m.cols, m.nnz, m.data.ctypes.data, m.row_offsets.ctypes.data, m.col_ids.ctypes.data)
+        arr = (ctypes.c_void_p * len(self.ctxs))(*[c.h for c in self.ctxs])
+        self.h = ctypes.c_void_p()
+        fn = self.lib.speck_b200_sharded_create_f32 if self.dtype == np.float32 else self.lib.speck_b200_sharded_create_f64
+        sa, sb_ = st(A), st(B)
+        _check(fn(arr, len(self.ctxs), ctypes.byref(sa), ctypes.byref(sb_), ctypes.byref(self.h)))
+        self.info = ShardInfoStruct()
+
+    def multiply(self):
+        _check(self.lib.speck_b200_sharded_multiply(self.h, ctypes.byref(self.info)))
+        return self.summary()
+
+    def concat(self, C: DeviceCSR = None) -> DeviceCSR:
+        if C is None:
+            C = DeviceCSR(self.ctxs[0], self.dtype)
+        _check(self.lib.speck_b200_sharded_concat(self.h, ctypes.byref(C.s), ctypes.byref(self.info)))
+        return C
+
+    def slab(self, g):
+        """Borrowed (A slab, C slab) device views on device g."""
+        a, c = DeviceCSR(self.ctxs[g], self.dtype), DeviceCSR(self.ctxs[g], self.dtype)
+        a.owned = c.owned = False
+        _check(self.lib.speck_b200_sharded_slab(self.h, int(g), ctypes.byref(a.s), ctypes.byref(c.s)))
+        return a, c
+
+    def summary(self):
+        i, n = self.info, self.info.shards
+        return {"shards": n, "cuts": list(i.cuts[:n + 1]), "products": list(i.products[:n]), "nnz_c": list(i.nnz_c[:n]),
+                "ms_device": list(i.ms_device[:n]), "ms_setup": i.ms_setup, "ms_multiply": i.ms_multiply,
+                "ms_concat": i.ms_concat, "concatenated": bool(i.concatenated)}
+
+    def close(self):
+        if self.h:
+            self.lib.speck_b200_sharded_destroy(self.h)
+            self.h = ctypes.c_void_p()
 
 
 def numeric_bytes(rows_a, nnz_a, products, nnz_c, val_bytes=8):

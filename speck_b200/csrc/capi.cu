@@ -11,10 +11,14 @@
 // Host<->device traffic per call: two 4-byte-class read-backs of one pinned Scalars struct
 // (after binning, after the scan) instead of the reference's 3-8 blocking copies, and no
 // cudaMalloc/cudaFree in the steady state (pooled workspace).
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/speck_b200.h"
 #include "common.cuh"
@@ -510,23 +514,55 @@ int spgemm_host_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck
 }
 
 template <typename T>
-int compare_impl(speck_ctx *c, const speck_csr *ref, const speck_csr *cmp, int compareData, double relTol)
+int compare_impl(speck_ctx *c, const speck_csr *ref, const speck_csr *cmp, int compareData, double relTol,
+                 speck_mismatch *first = nullptr)
 {
     if (!c || !ref || !cmp) return fail(SPECK_ERR_INVALID, "null argument");
-    if (ref->rows != cmp->rows || ref->cols != cmp->cols || ref->nnz != cmp->nnz) return 0;
-    if (ref->nnz == 0) return 1;
-    if (!ref->row_offsets || !cmp->row_offsets || !ref->col_ids || !cmp->col_ids) return 0;
+    if (first) *first = speck_mismatch{};
+    if (ref->rows != cmp->rows || ref->cols != cmp->cols || ref->nnz != cmp->nnz) {
+        if (first) first->kind = 3;
+        if (ref->rows != cmp->rows || ref->cols != cmp->cols || !first) return 0;
+    }
+    if (ref->nnz == 0 && cmp->nnz == 0) return 1;
+    if (!ref->row_offsets || !cmp->row_offsets || !ref->col_ids || !cmp->col_ids) {
+        if (first) first->kind = 3;
+        return 0;
+    }
     if (compareData && (!ref->data || !cmp->data)) return fail(SPECK_ERR_INVALID, "compare_data set but a value array is null");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemsetAsync(&c->dSc->compareFlag, 0, 4, c->main));
+    CU_TRY(cudaMemsetAsync(&c->dSc->compareFirst, 0xff, 8, c->main));
     u32 n = 0;
     LaunchCtx lc{c->main, c->smCount, &n};
     launch_compare<T>(lc, (u32)ref->rows, ref->row_offsets, ref->col_ids, (const T *)ref->data, cmp->row_offsets,
                       cmp->col_ids, (const T *)cmp->data, compareData != 0, relTol, c->dSc);
     CU_TRY(cudaMemcpyAsync(&c->hSc->compareFlag, &c->dSc->compareFlag, 4, cudaMemcpyDeviceToHost, c->main));
+    CU_TRY(cudaMemcpyAsync(&c->hSc->compareFirst, &c->dSc->compareFirst, 8, cudaMemcpyDeviceToHost, c->main));
     CU_TRY(cudaStreamSynchronize(c->main));
     CU_TRY(cudaGetLastError());
-    return c->hSc->compareFlag == 0 ? 1 : 0;
+    if (c->hSc->compareFlag == 0) return ref->nnz == cmp->nnz ? 1 : 0;
+    if (first) {   // details of the first difference: a handful of 4- and 8-byte reads
+        const u64 key = c->hSc->compareFirst;
+        const u32 row = (u32)(key >> 32), kind = (u32)(key >> 28) & 0xfu, pos = (u32)key & ((1u << 28) - 1u);
+        first->row = row;
+        first->kind = kind;
+        first->index_in_row = pos;
+        u32 ra[2] = {}, rb[2] = {};
+        CU_TRY(cudaMemcpy(ra, ref->row_offsets + row, 8, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(rb, cmp->row_offsets + row, 8, cudaMemcpyDeviceToHost));
+        first->ref_len = ra[1] - ra[0];
+        first->cmp_len = rb[1] - rb[0];
+        if (kind >= 1) {
+            CU_TRY(cudaMemcpy(&first->ref_col, ref->col_ids + ra[0] + pos, 4, cudaMemcpyDeviceToHost));
+            CU_TRY(cudaMemcpy(&first->cmp_col, cmp->col_ids + rb[0] + pos, 4, cudaMemcpyDeviceToHost));
+            T va = 0, vb = 0;
+            if (ref->data) CU_TRY(cudaMemcpy(&va, (const T *)ref->data + ra[0] + pos, sizeof(T), cudaMemcpyDeviceToHost));
+            if (cmp->data) CU_TRY(cudaMemcpy(&vb, (const T *)cmp->data + rb[0] + pos, sizeof(T), cudaMemcpyDeviceToHost));
+            first->ref_val = (double)va;
+            first->cmp_val = (double)vb;
+        }
+    }
+    return 0;
 }
 
 }  // namespace
@@ -673,6 +709,15 @@ int speck_b200_compare_f32(speck_ctx *c, const speck_csr *r, const speck_csr *m,
     return compare_impl<float>(c, r, m, cd, tol);
 }
 
+int speck_b200_compare_report_f64(speck_ctx *c, const speck_csr *r, const speck_csr *m, int cd, double tol, speck_mismatch *first)
+{
+    return compare_impl<double>(c, r, m, cd, tol, first);
+}
+int speck_b200_compare_report_f32(speck_ctx *c, const speck_csr *r, const speck_csr *m, int cd, double tol, speck_mismatch *first)
+{
+    return compare_impl<float>(c, r, m, cd, tol, first);
+}
+
 int speck_b200_malloc(speck_ctx *c, void **dptr, size_t bytes)
 {
     if (!c || !dptr) return fail(SPECK_ERR_INVALID, "null argument");
@@ -722,6 +767,313 @@ int speck_b200_synchronize(speck_ctx *c)
     return SPECK_OK;
 }
 void *speck_b200_stream(speck_ctx *c) { return c ? (void *)c->main : nullptr; }
+
+int speck_b200_partition_rows(speck_ctx *c, const speck_csr *A, const speck_csr *B, int parts, uint32_t *cuts,
+                              uint64_t *part_products)
+{
+    if (!c || !A || !B || !cuts) return fail(SPECK_ERR_INVALID, "null argument");
+    if (parts < 1 || parts > SPECK_MAX_SHARDS) return fail(SPECK_ERR_INVALID, "parts must be in [1, %d]", SPECK_MAX_SHARDS);
+    if (A->cols != B->rows) return fail(SPECK_ERR_INVALID, "shape mismatch: A is %zux%zu, B is %zux%zu", A->rows, A->cols, B->rows, B->cols);
+    CU_TRY(cudaSetDevice(c->device));
+    const u32 rows = (u32)A->rows;
+    cuts[0] = 0;
+    for (int g = 1; g <= parts; ++g) cuts[g] = rows;
+    if (part_products) memset(part_products, 0, sizeof(uint64_t) * parts);
+    if (rows == 0 || A->nnz == 0 || B->nnz == 0) {
+        for (int g = 1; g < parts; ++g) cuts[g] = (u32)(((u64)rows * g) / parts);
+        return SPECK_OK;
+    }
+    int rc;
+    if ((rc = ensure(c->rowOps, (size_t)(rows + 1) * 4))) return rc;
+    if ((rc = ensure(c->perm, (size_t)rows * 4))) return rc;   // scratch for the rowNnz side output
+    if ((rc = ensure(c->rowMin, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->rowMax, (size_t)rows * 4))) return rc;
+    if ((rc = ensure(c->mapBase, (size_t)(rows + 1) * 8 + (size_t)(parts + 1) * 4 + (size_t)parts * 8 + 16))) return rc;
+    if ((rc = ensure(c->tileState, scan_tile_state_bytes(rows + 1)))) return rc;
+    CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
+    u32 n = 0;
+    LaunchCtx lc{c->main, c->smCount, &n};
+    launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, B->col_ids, (u32 *)c->rowOps.p,
+                   (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax, nullptr, nullptr);
+    u64 *prefix = (u64 *)c->mapBase.p;
+    launch_scan_map(lc, (const u32 *)c->rowOps.p, prefix, rows + 1, (u64 *)c->tileState.p, c->dSc);
+    u64 *dPart = prefix + rows + 1;
+    u32 *dCuts = (u32 *)(dPart + parts);
+    launch_find_cuts(lc, prefix, rows, (u32)parts, dCuts, dPart);
+    CU_TRY(cudaMemcpyAsync(cuts, dCuts, (size_t)(parts + 1) * 4, cudaMemcpyDeviceToHost, c->main));
+    if (part_products) CU_TRY(cudaMemcpyAsync(part_products, dPart, (size_t)parts * 8, cudaMemcpyDeviceToHost, c->main));
+    CU_TRY(cudaStreamSynchronize(c->main));
+    CU_TRY(cudaGetLastError());
+    return SPECK_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Row-sharded multiply on several devices of one box.
+// ------------------------------------------------------------------------------------------------------------
+struct speck_shard_plan {
+    int n = 0;
+    size_t valBytes = 8;
+    speck_ctx *ctx[SPECK_MAX_SHARDS] = {};
+    speck_csr dA[SPECK_MAX_SHARDS] = {};   // slab of A on device g (row_offsets re-based)
+    speck_csr dB[SPECK_MAX_SHARDS] = {};   // B on device g
+    speck_csr dC[SPECK_MAX_SHARDS] = {};   // slab of C of the last multiply (reused)
+    u32 cuts[SPECK_MAX_SHARDS + 1] = {};
+    u64 products[SPECK_MAX_SHARDS] = {};
+    float msSetup = 0.f;
+    size_t rows = 0, colsB = 0;
+};
+
+namespace {
+
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void free_dev_csr(speck_csr &m)
+{
+    if (m.data) cudaFree(m.data);
+    if (m.col_ids) cudaFree(m.col_ids);
+    if (m.row_offsets) cudaFree(m.row_offsets);
+    m = speck_csr{};
+}
+
+int alloc_dev_csr(speck_csr &m, size_t rows, size_t cols, size_t nnz, size_t valBytes)
+{
+    m = speck_csr{};
+    m.rows = rows; m.cols = cols; m.nnz = nnz;
+    CU_TRY(cudaMalloc((void **)&m.row_offsets, (rows + 1) * 4));
+    CU_TRY(cudaMalloc((void **)&m.col_ids, (nnz ? nnz : 1) * 4));
+    CU_TRY(cudaMalloc(&m.data, (nnz ? nnz : 1) * valBytes));
+    return SPECK_OK;
+}
+
+template <typename T>
+int sharded_create_impl(speck_ctx **ctxs, int n, const speck_csr *A, const speck_csr *B, speck_shard_plan **out)
+{
+    if (!ctxs || !A || !B || !out) return fail(SPECK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (n < 1 || n > SPECK_MAX_SHARDS) return fail(SPECK_ERR_INVALID, "number of devices must be in [1, %d]", SPECK_MAX_SHARDS);
+    for (int g = 0; g < n; ++g) {   // several contexts may share a device (that is how the one-GPU tests run the slabs)
+        if (!ctxs[g]) return fail(SPECK_ERR_INVALID, "null context %d", g);
+        for (int h = 0; h < g; ++h)
+            if (ctxs[h] == ctxs[g]) return fail(SPECK_ERR_INVALID, "context %d is listed twice", g);
+    }
+    if (A->cols != B->rows) return fail(SPECK_ERR_INVALID, "shape mismatch: A is %zux%zu, B is %zux%zu", A->rows, A->cols, B->rows, B->cols);
+    if (!A->row_offsets || !B->row_offsets || (A->nnz && (!A->col_ids || !A->data)) || (B->nnz && (!B->col_ids || !B->data)))
+        return fail(SPECK_ERR_INVALID, "null CSR array");
+    speck_shard_plan *p = new (std::nothrow) speck_shard_plan();
+    if (!p) return fail(SPECK_ERR_OOM, "host allocation failed");
+    p->n = n;
+    p->valBytes = sizeof(T);
+    p->rows = A->rows;
+    p->colsB = B->cols;
+    for (int g = 0; g < n; ++g) p->ctx[g] = ctxs[g];
+    const double t0 = now_ms();
+    const int rc = [&]() -> int {
+        // B and (for the partition) the whole of A on the first device
+        speck_ctx *c0 = ctxs[0];
+        CU_TRY(cudaSetDevice(c0->device));
+        int rc;
+        if ((rc = alloc_dev_csr(p->dB[0], B->rows, B->cols, B->nnz, sizeof(T)))) return rc;
+        CU_TRY(cudaMemcpyAsync(p->dB[0].row_offsets, B->row_offsets, (B->rows + 1) * 4, cudaMemcpyHostToDevice, c0->main));
+        if (B->nnz) {
+            CU_TRY(cudaMemcpyAsync(p->dB[0].col_ids, B->col_ids, B->nnz * 4, cudaMemcpyHostToDevice, c0->main));
+            CU_TRY(cudaMemcpyAsync(p->dB[0].data, B->data, B->nnz * sizeof(T), cudaMemcpyHostToDevice, c0->main));
+        }
+        speck_csr fullA;
+        if ((rc = alloc_dev_csr(fullA, A->rows, A->cols, A->nnz, 1))) return rc;   // the partition reads indices only
+        CU_TRY(cudaMemcpyAsync(fullA.row_offsets, A->row_offsets, (A->rows + 1) * 4, cudaMemcpyHostToDevice, c0->main));
+        if (A->nnz) CU_TRY(cudaMemcpyAsync(fullA.col_ids, A->col_ids, A->nnz * 4, cudaMemcpyHostToDevice, c0->main));
+        rc = speck_b200_partition_rows(c0, &fullA, &p->dB[0], n, p->cuts, p->products);
+        free_dev_csr(fullA);
+        if (rc) return rc;
+        // B to the peers: device-to-device over NVLink (peer access is switched on when the pair supports it)
+        for (int g = 1; g < n; ++g) {
+            speck_ctx *cg = ctxs[g];
+            CU_TRY(cudaSetDevice(cg->device));
+            int can = 0;
+            if (cg->device != c0->device) cudaDeviceCanAccessPeer(&can, cg->device, c0->device);
+            if (can && cudaDeviceEnablePeerAccess(c0->device, 0) != cudaSuccess) cudaGetLastError();   // already enabled is fine
+            if ((rc = alloc_dev_csr(p->dB[g], B->rows, B->cols, B->nnz, sizeof(T)))) return rc;
+            CU_TRY(cudaMemcpyPeerAsync(p->dB[g].row_offsets, cg->device, p->dB[0].row_offsets, c0->device, (B->rows + 1) * 4, cg->main));
+            if (B->nnz) {
+                CU_TRY(cudaMemcpyPeerAsync(p->dB[g].col_ids, cg->device, p->dB[0].col_ids, c0->device, B->nnz * 4, cg->main));
+                CU_TRY(cudaMemcpyPeerAsync(p->dB[g].data, cg->device, p->dB[0].data, c0->device, B->nnz * sizeof(T), cg->main));
+            }
+        }
+        // slabs of A: row_offsets re-based on the host, column ids / values are contiguous slices
+        std::vector<u32> rp;
+        for (int g = 0; g < n; ++g) {
+            speck_ctx *cg = ctxs[g];
+            CU_TRY(cudaSetDevice(cg->device));
+            const u32 r0 = p->cuts[g], r1 = p->cuts[g + 1];
+            const u32 e0 = A->row_offsets[r0], e1 = A->row_offsets[r1];
+            if ((rc = alloc_dev_csr(p->dA[g], r1 - r0, A->cols, e1 - e0, sizeof(T)))) return rc;
+            rp.resize((size_t)(r1 - r0) + 1);
+            for (u32 i = 0; i <= r1 - r0; ++i) rp[i] = A->row_offsets[r0 + i] - e0;
+            CU_TRY(cudaMemcpyAsync(p->dA[g].row_offsets, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice, cg->main));
+            if (e1 > e0) {
+                CU_TRY(cudaMemcpyAsync(p->dA[g].col_ids, A->col_ids + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, cg->main));
+                CU_TRY(cudaMemcpyAsync(p->dA[g].data, (const T *)A->data + e0, (size_t)(e1 - e0) * sizeof(T), cudaMemcpyHostToDevice, cg->main));
+            }
+            CU_TRY(cudaStreamSynchronize(cg->main));   // rp is reused by the next slab
+        }
+        for (int g = 0; g < n; ++g) {
+            CU_TRY(cudaSetDevice(ctxs[g]->device));
+            CU_TRY(cudaStreamSynchronize(ctxs[g]->main));
+        }
+        return SPECK_OK;
+    }();
+    if (rc != SPECK_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        speck_b200_sharded_destroy(p);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    p->msSetup = (float)(now_ms() - t0);
+    *out = p;
+    return SPECK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int speck_b200_sharded_create_f64(speck_ctx **ctxs, int n, const speck_csr *A, const speck_csr *B, speck_shard_plan **plan)
+{
+    return sharded_create_impl<double>(ctxs, n, A, B, plan);
+}
+int speck_b200_sharded_create_f32(speck_ctx **ctxs, int n, const speck_csr *A, const speck_csr *B, speck_shard_plan **plan)
+{
+    return sharded_create_impl<float>(ctxs, n, A, B, plan);
+}
+
+int speck_b200_sharded_multiply(speck_shard_plan *p, speck_shard_info *info)
+{
+    if (!p) return fail(SPECK_ERR_INVALID, "null plan");
+    int rcs[SPECK_MAX_SHARDS] = {};
+    std::string errs[SPECK_MAX_SHARDS];
+    const double t0 = now_ms();
+    auto work = [&](int g) {
+        rcs[g] = p->valBytes == 4 ? spgemm_impl<float>(p->ctx[g], &p->dA[g], &p->dB[g], &p->dC[g], nullptr)
+                                  : spgemm_impl<double>(p->ctx[g], &p->dA[g], &p->dB[g], &p->dC[g], nullptr);
+        if (rcs[g]) errs[g] = g_err;   // the message lives in the worker thread's buffer
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < p->n; ++g) th.emplace_back(work, g);   // one host thread per device, the caller's thread drives device 0
+    work(0);
+    for (auto &t : th) t.join();
+    const double t1 = now_ms();
+    for (int g = 0; g < p->n; ++g)
+        if (rcs[g]) return fail(rcs[g], "shard %d (device %d): %s", g, p->ctx[g]->device, errs[g].c_str());
+    if (info) {
+        *info = speck_shard_info{};
+        info->shards = p->n;
+        for (int g = 0; g <= p->n; ++g) info->cuts[g] = p->cuts[g];
+        for (int g = 0; g < p->n; ++g) {
+            info->products[g] = p->ctx[g]->stats.products;
+            info->nnz_c[g] = p->dC[g].nnz;
+            info->ms_device[g] = p->ctx[g]->stats.ms_total;
+        }
+        info->ms_setup = p->msSetup;
+        info->ms_multiply = (float)(t1 - t0);
+    }
+    return SPECK_OK;
+}
+
+int speck_b200_sharded_concat(speck_shard_plan *p, speck_csr *C, speck_shard_info *info)
+{
+    if (!p || !C) return fail(SPECK_ERR_INVALID, "null argument");
+    const double t0 = now_ms();
+    speck_ctx *c0 = p->ctx[0];
+    u64 total = 0;
+    for (int g = 0; g < p->n; ++g) total += p->dC[g].nnz;
+    if (total > 0xffffffffull)
+        return fail(SPECK_ERR_OVERFLOW, "concatenated nnz(C) = %llu does not fit the u32 row_offsets of the spECK API: keep C distributed",
+                    (unsigned long long)total);
+    CU_TRY(cudaSetDevice(c0->device));
+    if (!(C->rows == p->rows && C->row_offsets)) {   // same reuse rules as spgemm_impl
+        if (C->row_offsets) cudaFree(C->row_offsets);
+        C->row_offsets = nullptr;
+        CU_TRY(cudaMalloc((void **)&C->row_offsets, (p->rows + 1) * 4));
+        C->rows = p->rows;
+    }
+    if (C->nnz != total || !C->data || !C->col_ids) {
+        if (C->data) cudaFree(C->data);
+        if (C->col_ids) cudaFree(C->col_ids);
+        C->data = nullptr; C->col_ids = nullptr; C->nnz = 0;
+        CU_TRY(cudaMalloc(&C->data, (total ? total : 1) * p->valBytes));
+        CU_TRY(cudaMalloc((void **)&C->col_ids, (total ? total : 1) * 4));
+    }
+    C->nnz = total;
+    C->cols = p->colsB;
+    int rc;
+    u32 maxRows = 0;
+    for (int g = 0; g < p->n; ++g) maxRows = max(maxRows, p->cuts[g + 1] - p->cuts[g]);
+    if ((rc = ensure(c0->stage[0], (size_t)(maxRows + 1) * 4))) return rc;   // landing buffer of a peer's row_offsets
+    u32 launches = 0;
+    LaunchCtx lc{c0->main, c0->smCount, &launches};
+    u64 base = 0;
+    for (int g = 0; g < p->n; ++g) {
+        const speck_csr &s = p->dC[g];
+        const u32 r0 = p->cuts[g], nr = p->cuts[g + 1] - p->cuts[g];
+        const int dev = p->ctx[g]->device;
+        if (s.nnz) {
+            CU_TRY(cudaMemcpyPeerAsync(C->col_ids + base, c0->device, s.col_ids, dev, s.nnz * 4, c0->main));
+            CU_TRY(cudaMemcpyPeerAsync((char *)C->data + base * p->valBytes, c0->device, s.data, dev, s.nnz * p->valBytes, c0->main));
+        }
+        if (s.nnz && s.row_offsets) {
+            const u32 *src = s.row_offsets;
+            if (g > 0) {
+                CU_TRY(cudaMemcpyPeerAsync(c0->stage[0].p, c0->device, s.row_offsets, dev, (size_t)(nr + 1) * 4, c0->main));
+                src = (const u32 *)c0->stage[0].p;
+            }
+            launch_offset_rows(lc, src, nr + (g == p->n - 1 ? 1u : 0u), (u32)base, C->row_offsets + r0);
+        } else {   // empty slab: every row starts (and the slab ends) at base
+            std::vector<u32> fill((size_t)nr + 1, (u32)base);
+            CU_TRY(cudaMemcpyAsync(C->row_offsets + r0, fill.data(), fill.size() * 4, cudaMemcpyHostToDevice, c0->main));
+            CU_TRY(cudaStreamSynchronize(c0->main));
+        }
+        base += s.nnz;
+    }
+    // the last slab wrote row_offsets[rows] = total only when it was not empty
+    const u32 tot32 = (u32)total;
+    CU_TRY(cudaMemcpyAsync(C->row_offsets + p->rows, &tot32, 4, cudaMemcpyHostToDevice, c0->main));
+    CU_TRY(cudaStreamSynchronize(c0->main));
+    CU_TRY(cudaGetLastError());
+    if (info) {
+        info->concatenated = 1;
+        info->ms_concat = (float)(now_ms() - t0);
+    }
+    return SPECK_OK;
+}
+
+int speck_b200_sharded_slab(speck_shard_plan *p, int g, speck_csr *A_slab, speck_csr *C_slab)
+{
+    if (!p || g < 0 || g >= p->n) return fail(SPECK_ERR_INVALID, "bad plan or slab index");
+    if (A_slab) *A_slab = p->dA[g];
+    if (C_slab) *C_slab = p->dC[g];
+    return SPECK_OK;
+}
+
+int speck_b200_sharded_destroy(speck_shard_plan *p)
+{
+    if (!p) return SPECK_OK;
+    for (int g = 0; g < p->n; ++g) {
+        if (!p->ctx[g]) continue;
+        cudaSetDevice(p->ctx[g]->device);
+        cudaDeviceSynchronize();
+        free_dev_csr(p->dA[g]);
+        free_dev_csr(p->dB[g]);
+        free_dev_csr(p->dC[g]);
+    }
+    delete p;
+    return SPECK_OK;
+}
 
 int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
 {
@@ -782,6 +1134,10 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         cudaDeviceSynchronize();
         release(c->rowOps); release(c->perm); release(c->rowMin); release(c->rowMax); release(c->tileState); release(c->bitmapStore); release(c->mapLen); release(c->mapBase); release(c->rankMap); release(c->aSeg); release(c->aOff); release(c->desc); release(c->rowInfo);
         for (auto &b : c->stage) release(b);
+        if (c->hostC.data) cudaFree(c->hostC.data);       // device C kept by the *_host entry points
+        if (c->hostC.col_ids) cudaFree(c->hostC.col_ids);
+        if (c->hostC.row_offsets) cudaFree(c->hostC.row_offsets);
+        c->hostC = speck_csr{};
         return SPECK_OK;
     }
     return fail(SPECK_ERR_INVALID, "unknown option '%s'", key);

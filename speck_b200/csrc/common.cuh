@@ -51,6 +51,8 @@ struct Scalars {
     u32 mapTileCounter;       // dynamic tile ids of the rank-map offset scan
     u64 mapTotal;             // entries of the rank map (products of all mapped rows)
     u32 compareFlag;          // k_compare: 0 = equal
+    u64 compareFirst;         // k_compare: smallest (row << 32 | kind << 28 | position in row) that differs; kind 0 = row
+                              // length, 1 = column id, 2 = value (first-mismatch report)
 };
 
 // Row descriptor of the mapped classes, one per binned row in perm order (built once per multiply): a CTA /
@@ -114,6 +116,11 @@ void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trai
                  u64 *tileState, Scalars *sc);
 // exclusive scan of in[0..n-1) into 64-bit out[0..n) (out[n-1] = total, also stored in sc->mapTotal)
 void launch_scan_map(const LaunchCtx &lc, const u32 *in, u64 *out, u32 n, u64 *tileState, Scalars *sc);
+
+// multi-GPU helpers: product-balanced row cuts from the u64 prefix of rowOps (prefix[rows] = P); row_offsets of a
+// slab shifted by the slab's first position in the concatenated C
+void launch_find_cuts(const LaunchCtx &lc, const u64 *prefix, u32 rows, u32 parts, u32 *cuts, u64 *partProducts);
+void launch_offset_rows(const LaunchCtx &lc, const u32 *in, u32 n, u32 base, u32 *out);
 
 // Rank map: one u16 per product of a mapped row, written by the symbolic phase at mapBase[row] + (index of the
 // product in the row's flat enumeration: A entries ascending, then B-row order):

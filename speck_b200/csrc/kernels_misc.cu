@@ -369,6 +369,53 @@ void launch_scan_map(const LaunchCtx &lc, const u32 *in, u64 *out, u32 n, u64 *t
 }
 
 // ------------------------------------------------------------------------------------------
+// Multi-GPU helpers (no reference counterpart: the reference is single-device).
+//   k_find_cuts:   contiguous row cuts balanced by products: cut g = first row whose exclusive product prefix
+//                  reaches g * P / parts (prefix = the u64 scan of rowOps), cuts[0] = 0, cuts[parts] = rows
+//   k_offset_rows: row_offsets of slab g of the concatenated C: out[i] = in[i] + base
+// ------------------------------------------------------------------------------------------
+__global__ void k_find_cuts(const u64 *__restrict__ prefix, u32 rows, u32 parts, u32 *__restrict__ cuts,
+                            u64 *__restrict__ partProducts)
+{
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > parts) return;
+    const u64 total = prefix[rows];
+    auto cut_of = [&](u32 part) -> u32 {
+        if (part == 0) return 0u;
+        if (part >= parts) return rows;
+        const u64 target = (u64)(((unsigned __int128)total * part) / parts);
+        u32 lo = 0, hi = rows;   // first r with prefix[r] >= target
+        while (lo < hi) {
+            const u32 mid = lo + (hi - lo) / 2;
+            if (prefix[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const u32 c = cut_of(g);
+    cuts[g] = c;
+    if (g < parts && partProducts) partProducts[g] = prefix[cut_of(g + 1)] - prefix[c];
+}
+
+void launch_find_cuts(const LaunchCtx &lc, const u64 *prefix, u32 rows, u32 parts, u32 *cuts, u64 *partProducts)
+{
+    k_find_cuts<<<(parts + 1 + 63) / 64, 64, 0, lc.stream>>>(prefix, rows, parts, cuts, partProducts);
+    ++*lc.launches;
+}
+
+__global__ void __launch_bounds__(256) k_offset_rows(const u32 *__restrict__ in, u32 n, u32 base, u32 *__restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + base;
+}
+
+void launch_offset_rows(const LaunchCtx &lc, const u32 *in, u32 n, u32 base, u32 *out)
+{
+    if (n == 0) return;
+    k_offset_rows<<<(n + 255) / 256, 256, 0, lc.stream>>>(in, n, base, out);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------
 // Direct rows: A row with one entry -> C row = a_ik * B_k, already sorted.
 // (reference: directSpGEMMNumericImplementation, spECK_HashSpGEMM.cuh:543-569)
 // ------------------------------------------------------------------------------------------
@@ -428,18 +475,24 @@ __global__ void __launch_bounds__(256) k_compare(u32 rows, const u32 *__restrict
     const u32 lane = threadIdx.x & 31;
     if (row >= rows) return;
     const u32 a0 = rpA[row], a1 = rpA[row + 1], b0 = rpB[row], b1 = rpB[row + 1];
-    bool bad = (a1 - a0) != (b1 - b0);
-    if (!bad) {
-        for (u32 j = lane; j < a1 - a0; j += 32) {
-            if (ciA[a0 + j] != ciB[b0 + j]) bad = true;
-            if (compareData) {
+    u64 first = ~0ull;   // smallest differing (row, kind, position) seen by this lane
+    if ((a1 - a0) != (b1 - b0)) {
+        first = (u64)row << 32;
+    } else {
+        for (u32 j = lane; j < a1 - a0 && first == ~0ull; j += 32) {
+            const u32 pos = j < (1u << 28) ? j : (1u << 28) - 1u;
+            if (ciA[a0 + j] != ciB[b0 + j]) first = ((u64)row << 32) | (1u << 28) | pos;
+            else if (compareData) {
                 const double x = (double)vA[a0 + j], y = (double)vB[b0 + j];
                 const double d = fabs(x - y), s = fmax(fabs(x), fabs(y));
-                if (d > relTol * s && d > 1e-300) bad = true;
+                if (d > relTol * s && d > 1e-300) first = ((u64)row << 32) | (2u << 28) | pos;
             }
         }
     }
-    if (bad) sc->compareFlag = 1u;
+    if (first != ~0ull) {
+        sc->compareFlag = 1u;
+        atomicMin((unsigned long long *)&sc->compareFirst, (unsigned long long)first);
+    }
 }
 
 template <typename T>

@@ -39,6 +39,7 @@ const char *Config::name(Key key)
         case TrackCompleteTimes: return "trackcompletetimes";
         case CompareResult: return "compareresult";
         case Device: return "device";
+        case Devices: return "devices";
     }
     return "";
 }

@@ -222,6 +222,140 @@ def test_fp32(ctx):
     assert_csr_equal(got, want, rtol=2e-5, what="fp32")
 
 
+def test_fp32_every_kernel_family(ctx, sort_max):
+    """fp32 through the same kernel-family switch as the fp64 cases (rank / flat rank / CTA sort / bitmap / mapped
+    and self-contained numeric kernels)."""
+    A = M.rmat(14, 16, seed=9, dtype=np.float32)
+    got, st = gpu_multiply(ctx, A)
+    want = oracle_multiply(A.astype(np.float64), A.astype(np.float64))
+    assert got.data.dtype == np.float32
+    assert_csr_equal(got, want, rtol=1e-4, what=f"fp32 rmat14 sort_max={sort_max}")
+    B = M.banded_fem_like(n=3000, per_row=48, clusters=6, band=200, seed=8, dtype=np.float32)
+    got, st = gpu_multiply(ctx, B)
+    assert_csr_equal(got, oracle_multiply(B.astype(np.float64), B.astype(np.float64)), rtol=1e-4, what="fp32 banded")
+
+
+# ---------------------------------------------------------------- error paths (reference: source/GPU/Multiply.cu:57-97)
+def _csr_struct(api, rows, cols, nnz, data=None, rp=None, ci=None):
+    return api.CsrStruct(rows, cols, nnz, data, rp, ci)
+
+
+def test_error_too_large_and_shape_mismatch(ctx):
+    """rows(A) or cols(B) above 2^27 -> SPECK_ERR_TOO_LARGE before anything is touched (Multiply.cu:57-66); A.cols
+    != B.rows -> SPECK_ERR_INVALID; C is left untouched in every case."""
+    import ctypes
+    from speck_b200 import api
+    A = M.uniform_random(64, 64, 3, seed=1)
+    dA = ctx.upload(A)
+    C = api.DeviceCSR(ctx)
+    big_rows = _csr_struct(api, (1 << 27) + 1, 64, dA.s.nnz, dA.s.data, dA.s.row_offsets, dA.s.col_ids)
+    big_cols = _csr_struct(api, 64, (1 << 27) + 1, dA.s.nnz, dA.s.data, dA.s.row_offsets, dA.s.col_ids)
+    lib = ctx.lib
+    rc = lib.speck_b200_spgemm_f64(ctx.h, ctypes.byref(big_rows), ctypes.byref(dA.s), ctypes.byref(C.s), None)
+    assert rc == -2 and b"rows" in lib.speck_b200_last_error()
+    rc = lib.speck_b200_spgemm_f64(ctx.h, ctypes.byref(dA.s), ctypes.byref(big_cols), ctypes.byref(C.s), None)
+    assert rc == -2 and b"columns" in lib.speck_b200_last_error()
+    wrong = _csr_struct(api, 63, 64, dA.s.nnz, dA.s.data, dA.s.row_offsets, dA.s.col_ids)
+    rc = lib.speck_b200_spgemm_f64(ctx.h, ctypes.byref(dA.s), ctypes.byref(wrong), ctypes.byref(C.s), None)
+    assert rc == -1 and b"shape mismatch" in lib.speck_b200_last_error()
+    rc = lib.speck_b200_spgemm_f64(ctx.h, None, ctypes.byref(dA.s), ctypes.byref(C.s), None)
+    assert rc == -1
+    assert (C.s.rows, C.s.nnz, C.s.data, C.s.col_ids, C.s.row_offsets) == (0, 0, None, None, None)
+    with pytest.raises(api.SpeckError):
+        ctx.set_option("no_such_option", 1)
+    with pytest.raises(api.SpeckError):
+        ctx.set_option("sort_max", 1000)
+    # the context still works after the errors
+    check_case(ctx, A, what="after errors")
+    dA.free()
+
+
+def test_error_nnz_overflow(ctx):
+    """nnz(C) >= 2^32 does not fit the u32 row_offsets of the spECK API -> SPECK_ERR_OVERFLOW after the symbolic
+    phase (the reference overflows silently).  A = 70000 rows of 1 entry hitting one dense
+    B row of 2^16 columns: P = nnz(C) = 4.59e9, found by the analysis alone (direct rows need no symbolic kernel)."""
+    import ctypes
+    from speck_b200 import api
+    rowsA, n = 70000, 1 << 16
+    A = HostCSR(rowsA, 4, np.arange(rowsA + 1, dtype=np.uint32), np.zeros(rowsA, np.uint32), np.ones(rowsA))
+    brp = np.array([0, n, n, n, n], np.uint32)
+    B = HostCSR(4, n, brp, np.arange(n, dtype=np.uint32), np.ones(n))
+    dA, dB = ctx.upload(A), ctx.upload(B)
+    C = api.DeviceCSR(ctx)
+    rc = ctx.lib.speck_b200_spgemm_f64(ctx.h, ctypes.byref(dA.s), ctypes.byref(dB.s), ctypes.byref(C.s), None)
+    assert rc == -3, ctx.lib.speck_b200_last_error()
+    assert b"does not fit" in ctx.lib.speck_b200_last_error()
+    assert C.s.data is None and C.s.col_ids is None    # nothing was allocated for the oversized result
+    C.free(), dA.free(), dB.free()
+    check_case(ctx, M.uniform_random(100, 100, 4, seed=2), what="after overflow")
+
+
+def test_error_out_of_memory_for_c(ctx):
+    """C larger than the free device memory -> SPECK_ERR_OOM, C->data / col_ids left NULL (reference: prints
+    'ERROR: out of memory' and returns, Multiply.cu:594-599); the context stays usable."""
+    import ctypes
+    import torch
+    from speck_b200 import api
+    free_b, _ = torch.cuda.mem_get_info(0)
+    # nnz(C) = rowsA * n just below 2^32 needs 12 * 4.29e9 = 51.5 GB: hog memory so that less than that is free
+    hog = []
+    need = 51.5e9
+    try:
+        while free_b > need - (4 << 30) and free_b > (8 << 30):
+            take = int(min(free_b - (need - (8 << 30)), 32 << 30))
+            if take < (1 << 30):
+                break
+            hog.append(torch.empty(take, dtype=torch.uint8, device="cuda:0"))
+            free_b, _ = torch.cuda.mem_get_info(0)
+        rowsA, n = 65535, 1 << 16
+        A = HostCSR(rowsA, 4, np.arange(rowsA + 1, dtype=np.uint32), np.zeros(rowsA, np.uint32), np.ones(rowsA))
+        B = HostCSR(4, n, np.array([0, n, n, n, n], np.uint32), np.arange(n, dtype=np.uint32), np.ones(n))
+        dA, dB = ctx.upload(A), ctx.upload(B)
+        C = api.DeviceCSR(ctx)
+        rc = ctx.lib.speck_b200_spgemm_f64(ctx.h, ctypes.byref(dA.s), ctypes.byref(dB.s), ctypes.byref(C.s), None)
+        assert rc == -5, (rc, ctx.lib.speck_b200_last_error())
+        assert C.s.data is None and C.s.col_ids is None and C.s.nnz == 0
+        C.free(), dA.free(), dB.free()
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+    check_case(ctx, M.uniform_random(100, 100, 4, seed=3), what="after OOM")
+
+
+def test_host_entry_dtype_switch_and_empty_product(ctx):
+    """One context, host entry: f32 then f64 with the same nnz(C) must not reuse the smaller value buffer (advisor
+    finding, round 1); an empty product returns a well-formed CSR (zero row_offsets of rows + 1 entries)."""
+    A64 = M.rmat(11, 8, seed=12)
+    A32 = A64.astype(np.float32)
+    got32, _, _ = ctx.multiply_host(A32, A32)
+    got32 = HostCSR(got32.rows, got32.cols, got32.row_offsets.copy(), got32.col_ids.copy(), got32.data.copy())
+    got64, _, _ = ctx.multiply_host(A64, A64)
+    want = oracle_multiply(A64, A64)
+    assert_csr_equal(HostCSR(got64.rows, got64.cols, got64.row_offsets.copy(), got64.col_ids.copy(), got64.data.copy()),
+                     want, what="host f64 after f32")
+    assert_csr_equal(got32, want, rtol=1e-4, what="host f32")
+    Z = HostCSR(300, A64.rows, np.zeros(301, np.uint32), np.zeros(0, np.uint32), np.zeros(0))
+    got, _, _ = ctx.multiply_host(Z, A64)
+    assert got.rows == 300 and got.nnz == 0 and got.row_offsets.shape == (301,) and not got.row_offsets.any()
+    # P == 0 with non-empty operands: A only references empty rows of B
+    Bz = HostCSR(4, 8, np.array([0, 0, 0, 0, 3], np.uint32), np.array([1, 2, 5], np.uint32), np.ones(3))
+    Az = HostCSR(3, 4, np.array([0, 1, 2, 3], np.uint32), np.array([0, 1, 2], np.uint32), np.ones(3))
+    got, _, _ = ctx.multiply_host(Az, Bz)
+    assert got.rows == 3 and got.nnz == 0 and not got.row_offsets.any()
+
+
+def test_api_rejects_mixed_dtypes(ctx):
+    from speck_b200 import api
+    A = M.uniform_random(50, 50, 3, seed=1)
+    d64, d32 = ctx.upload(A), ctx.upload(A.astype(np.float32))
+    with pytest.raises(api.SpeckError):
+        ctx.multiply(d64, d32)
+    C = ctx.multiply(d64, d64)
+    with pytest.raises(api.SpeckError):
+        ctx.multiply(d32, d32, C)      # C holds f64 values
+    C.free(), d64.free(), d32.free()
+
+
 def test_c_reuse_semantics(ctx):
     """C is reused across calls when nnz is unchanged (Multiply.cu:155-165, 589-592)."""
     A = M.rmat(11, 8, seed=4)
@@ -348,3 +482,91 @@ def test_rank_map_allocation_fallback(ctx, cols):
     assert st["class_rows"]["sort16384"] == 2
     got2, st2 = check_case(ctx, A, B, what=f"mapped cols={cols}")
     assert_csr_equal(got, got2, what="fallback vs mapped")
+
+
+def test_compare_reports_first_mismatch(ctx):
+    """speck_b200_compare_report: the first differing (row, kind, position), which the reference's d_compare
+    (source/GPU/Compare.cu:27-58) cannot tell."""
+    A = M.rmat(10, 8, seed=1)
+    C = oracle_multiply(A, A)
+    dRef = ctx.upload(C)
+    eq, mm = ctx.compare_report(dRef, dRef, True)
+    assert eq and mm is None
+    # a wrong value in row 700, a wrong column in row 300: the column error comes first
+    row_v, row_c = 700, 300
+    bad = HostCSR(C.rows, C.cols, C.row_offsets.copy(), C.col_ids.copy(), C.data.copy())
+    pv = int(C.row_offsets[row_v]) + 2
+    bad.data[pv] *= 1.5
+    dBad = ctx.upload(bad)
+    eq, mm = ctx.compare_report(dRef, dBad, True, 1e-6)
+    assert not eq and (mm["row"], mm["kind"], mm["index_in_row"]) == (row_v, 2, 2)
+    assert mm["ref_val"] == C.data[pv] and mm["cmp_val"] == bad.data[pv] and mm["ref_col"] == C.col_ids[pv]
+    assert ctx.compare(dRef, dBad, False) and not ctx.compare(dRef, dBad, True)
+    dBad.free()
+    pc = int(C.row_offsets[row_c]) + 1
+    bad.col_ids[pc] += 1 if bad.col_ids[pc] + 1 != bad.col_ids[min(pc + 1, C.nnz - 1)] else 2
+    dBad = ctx.upload(bad)
+    eq, mm = ctx.compare_report(dRef, dBad, True, 1e-6)
+    assert not eq and (mm["row"], mm["kind"], mm["index_in_row"]) == (row_c, 1, 1)
+    assert mm["ref_col"] == C.col_ids[pc] and mm["cmp_col"] == bad.col_ids[pc]
+    dBad.free()
+    # a row length error (one entry moved from row 100 to row 101) comes before both
+    rp = C.row_offsets.copy()
+    rp[101] -= 1
+    dBad = ctx.upload(HostCSR(C.rows, C.cols, rp, C.col_ids, C.data))
+    eq, mm = ctx.compare_report(dRef, dBad, False)
+    assert not eq and (mm["row"], mm["kind"]) == (100, 0) and mm["ref_len"] == mm["cmp_len"] + 1
+    dBad.free(), dRef.free()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gpu_coo_to_csr(ctx, dtype):
+    """GPU-side COO -> CSR (loader path) against the host conversion: sorted by (row, column),
+    stable; duplicates kept (the reference's loader, source/CSR.cpp:173-212) or summed in input order."""
+    rng = np.random.default_rng(3)
+    rows, cols, n = 5000, 3000, 200_000
+    r = rng.integers(0, rows, n).astype(np.uint32)
+    r[r % 7 == 3] = 11                       # many empty rows, one heavy row
+    c = rng.integers(0, cols, n).astype(np.uint32)
+    c[::5] = c[1::5][: c[::5].size]          # plenty of duplicate (row, col) candidates
+    r[::5] = r[1::5][: r[::5].size]
+    v = rng.standard_normal(n).astype(dtype)
+    order = np.lexsort((np.arange(n), c, r))  # stable by (row, col)
+    # KEEP
+    d = ctx.coo_to_csr(rows, cols, r, c, v, sum_duplicates=False)
+    got = ctx.download(d)
+    d.free()
+    want_rp = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=rows))]).astype(np.uint32)
+    np.testing.assert_array_equal(got.row_offsets, want_rp)
+    np.testing.assert_array_equal(got.col_ids, c[order])
+    np.testing.assert_array_equal(got.data, v[order])
+    # SUM: runs of equal (row, col) folded in input order
+    d = ctx.coo_to_csr(rows, cols, r, c, v, sum_duplicates=True)
+    got = ctx.download(d)
+    d.free()
+    key = r[order].astype(np.int64) * cols + c[order]
+    head = np.concatenate([[True], key[1:] != key[:-1]])
+    starts = np.flatnonzero(head)
+    want_v = np.array([np.add.reduce(v[order][s:e], dtype=dtype) if False else _seq_sum(v[order][s:e]) for s, e in zip(starts, np.append(starts[1:], n))], dtype=dtype)
+    np.testing.assert_array_equal(got.col_ids, c[order][head])
+    np.testing.assert_array_equal(got.row_offsets, np.concatenate([[0], np.cumsum(np.bincount(r[order][head], minlength=rows))]).astype(np.uint32))
+    np.testing.assert_array_equal(got.data, want_v)
+    assert got.nnz == int(head.sum()) < n
+    # the summed form is a valid multiply operand
+    sq = ctx.coo_to_csr(rows, rows, r, c % rows, v.astype(np.float64), sum_duplicates=True)
+    h = ctx.download(sq)
+    C = ctx.multiply(sq, sq)
+    assert_csr_equal(ctx.download(C), oracle_multiply(h, h), what="A.A of a GPU-converted matrix")
+    C.free(), sq.free()
+    # empty input
+    e = ctx.coo_to_csr(10, 10, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, dtype))
+    he = ctx.download(e)
+    assert he.nnz == 0 and not he.row_offsets.any()
+    e.free()
+
+
+def _seq_sum(x):
+    s = x[0]
+    for t in x[1:]:
+        s = s + t        # same type, left to right: the order the kernel uses
+    return s
