@@ -453,30 +453,42 @@ def main():
                 g_rp = torch.empty(A.rows + 1, dtype=torch.int32, device=dev)
                 g_ci = torch.empty(total, dtype=torch.int32, device=dev)
                 g_v = torch.empty(total, dtype=torch.float64, device=dev)
+            # NCCL point-to-point connections are set up lazily on first use: warm them up outside the timed region
+            warm = torch.zeros(4, dtype=torch.int32, device=dev)
+            ops = ([dist.P2POp(dist.irecv, torch.zeros(4, dtype=torch.int32, device=dev), r) for r in range(1, world)]
+                   if rank == 0 else [dist.P2POp(dist.isend, warm, 0)])
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if rank == 0:
-                base = 0
+                # every slab lands at its final position (one grouped NCCL receive), row_offsets get the slab's base added
+                tmp_rp, ops, base, bases = {}, [], 0, []
                 for r in range(world):
                     r0, r1 = int(cuts[r]), int(cuts[r + 1])
-                    if r == 0:
-                        g_ci[:cnt[0]] = c_ci
-                        g_v[:cnt[0]] = c_v
-                        g_rp[r0:r1 + 1] = c_rp
-                    else:
-                        tmp = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=dev)
-                        dist.recv(tmp, r)
+                    bases.append(base)
+                    if r > 0:
+                        tmp_rp[r] = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=dev)
+                        ops.append(dist.P2POp(dist.irecv, tmp_rp[r], r))
                         if cnt[r]:
-                            dist.recv(g_ci[base:base + cnt[r]], r)
-                            dist.recv(g_v[base:base + cnt[r]], r)
-                        g_rp[r0:r1 + 1] = tmp + base    # offset fix-up (values below 2^32 wrap correctly in int32)
+                            ops.append(dist.P2POp(dist.irecv, g_ci[base:base + cnt[r]], r))
+                            ops.append(dist.P2POp(dist.irecv, g_v[base:base + cnt[r]], r))
                     base += cnt[r]
+                works = dist.batch_isend_irecv(ops) if ops else []
+                g_ci[:cnt[0]] = c_ci
+                g_v[:cnt[0]] = c_v
+                g_rp[int(cuts[0]):int(cuts[1]) + 1] = c_rp
+                for w in works:
+                    w.wait()
+                for r in range(1, world):     # offset fix-up (values below 2^32 wrap correctly in int32)
+                    g_rp[int(cuts[r]):int(cuts[r + 1]) + 1] = tmp_rp[r] + bases[r]
             else:
-                dist.send(c_rp, 0)
+                ops = [dist.P2POp(dist.isend, c_rp, 0)]
                 if nnzC:
-                    dist.send(c_ci, 0)
-                    dist.send(c_v, 0)
+                    ops += [dist.P2POp(dist.isend, c_ci, 0), dist.P2POp(dist.isend, c_v, 0)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
             e1.record()
             barrier()
             concat_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -63,7 +63,10 @@ struct speck_ctx {
     cudaEvent_t evFork = nullptr, evJoin[NSIDE] = {};
     cudaEvent_t evStage[6] = {};
     Scalars *dSc = nullptr;
-    Scalars *hSc = nullptr;  // pinned
+    Scalars *hSc = nullptr;  // pinned, mapped: written by k_publish (or by a plain D2H copy when spinWait is off)
+    volatile u32 *hSeq = nullptr;   // sequence word next to the mirror, polled by the host
+    u32 seq = 0;
+    bool spinWait = true;    // mid-pipeline read-backs: poll the mapped mirror instead of cudaStreamSynchronize
     DevBuf rowOps, rowMin, rowMax, perm, tileState, bitmapStore, mapLen, mapBase, rankMap, aSeg, aOff, desc, rowInfo;
     DevBuf stage[6];          // device staging of the *_host entry points (A: rp, ci, v; B: rp, ci, v)
     void *hostOut[3] = {};    // pinned output buffers of the *_host entry points
@@ -80,6 +83,8 @@ struct speck_ctx {
     size_t rankMapMaxBytes = ~(size_t)0;  // test hook: larger maps are treated as "does not fit" (exercises the fallbacks)
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
+    int denseSeq = 1;         // banded / high-compression rows: sequential-k numeric kernel (dense_seq.cuh): 0 = off,
+                              // 1 = B segments loaded by the lanes, 2 = staged by TMA bulk copies
     int segNum = 0;           // mapped numeric CTA classes: 1 = segment-major kernel (map_seg.cuh; measured slower: fewer
                               // loads in flight per SM, profiles/r2_notes.md), 0 = k_map_rows_cta
     int flatSym = 1;          // mapped two-level symbolic rank kernel: 1 = flat staged variant (rank_flat.cuh), 0 = rank_cta.cuh
@@ -124,6 +129,33 @@ bool sort_keys_wide(int sc, u32 colsB)
         while (npow2 < 512u * (u32)(sc - NUM_WARP_SORT + 2)) npow2 <<= 1;
     }
     return ((u64)colsB * npow2) > (1ull << 32);
+}
+
+// Scalars to the host in the middle of a multiply.  Polling a word in mapped pinned memory costs 2-3 us against
+// ~15-20 us for cudaMemcpyAsync + cudaStreamSynchronize; the stream is queried now and then so that a failed
+// kernel cannot hang the host.
+int read_scalars(speck_ctx *c, LaunchCtx &lc)
+{
+    if (!c->spinWait) {
+        CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
+        CU_TRY(cudaStreamSynchronize(c->main));
+        return SPECK_OK;
+    }
+    const u32 seq = ++c->seq;
+    launch_publish(lc, c->dSc, c->hSc, c->hSeq, seq);
+    for (u64 spins = 0;; ++spins) {
+        if (*c->hSeq == seq) break;
+        if ((spins & 0x3fff) == 0x3fff) {
+            const cudaError_t q = cudaStreamQuery(c->main);
+            if (q != cudaErrorNotReady && *c->hSeq != seq) {   // the stream drained (or failed) without publishing
+                if (q != cudaSuccess) return fail(SPECK_ERR_CUDA, "kernel failure before the scalar read-back: %s", cudaGetErrorString(q));
+                CU_TRY(cudaStreamSynchronize(c->main));
+                if (*c->hSeq == seq) break;
+                return fail(SPECK_ERR_CUDA, "scalar read-back was not published");
+            }
+        }
+    }
+    return SPECK_OK;
 }
 
 void fork_streams(speck_ctx *c)
@@ -213,9 +245,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (u32 *)c->mapLen.p : nullptr,
                        useRank, c->mapMinClass);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
-    CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
     cudaEventRecord(c->evStage[1], c->main);
-    CU_TRY(cudaStreamSynchronize(c->main));
+    if ((rc = read_scalars(c, lc))) return rc;
     const Scalars s1 = *c->hSc;
     if (s1.products == 0) {  // Multiply.cu:256-261: alloc(rows, cols, 0, false)
         if (C->data) cudaFree(C->data);
@@ -313,9 +344,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
 
     // ---- scan + nnz read-back
     launch_scan(lc, cRp, rows + 1, (u64 *)c->tileState.p, c->dSc);
-    CU_TRY(cudaMemcpyAsync(&c->hSc->nnzC, &c->dSc->nnzC, sizeof(u64), cudaMemcpyDeviceToHost, c->main));
     cudaEventRecord(c->evStage[3], c->main);
-    CU_TRY(cudaStreamSynchronize(c->main));
+    if ((rc = read_scalars(c, lc))) return rc;
     CU_TRY(cudaGetLastError());
     const u64 nnzC = c->hSc->nnzC;
     if (nnzC > 0xffffffffull) return fail(SPECK_ERR_OVERFLOW, "nnz(C) = %llu does not fit the u32 row_offsets of the spECK API", (unsigned long long)nnzC);
@@ -351,7 +381,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (!s1.binCount[bin]) continue;
         LaunchCtx ls{c->side[NSIDE - 1], c->smCount, &c->launches};
         launch_dense_numeric<T>(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[2 + loc],
-                                aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV);
+                                aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV,
+                                c->denseSeq, rowOps);
     }
     if (useRank) {
         for (int g = RANK_GROUPS - 1; g >= 0; --g) {
@@ -605,7 +636,9 @@ int speck_b200_create(int device, speck_ctx **out)
         CU_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
         for (auto &e : c->evStage) CU_TRY(cudaEventCreate(&e));
         CU_TRY(cudaMalloc(&c->dSc, sizeof(Scalars)));
-        CU_TRY(cudaMallocHost(&c->hSc, sizeof(Scalars)));
+        CU_TRY(cudaHostAlloc(&c->hSc, sizeof(Scalars) + 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(c->hSc, 0, sizeof(Scalars) + 64);
+        c->hSeq = reinterpret_cast<volatile u32 *>(reinterpret_cast<char *>(c->hSc) + ((sizeof(Scalars) + 15) / 16) * 16);
         return SPECK_OK;
     }();
     if (rc != SPECK_OK) {   // do not leak the partially built context
@@ -1106,6 +1139,15 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     }
     if (!strcmp(key, "rank_map")) {
         c->rankMapOn = value != 0;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "dense_seq")) {
+        if (value < 0 || value > 2) return fail(SPECK_ERR_INVALID, "dense_seq must be 0, 1 or 2");
+        c->denseSeq = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "spin_wait")) {
+        c->spinWait = value != 0;
         return SPECK_OK;
     }
     if (!strcmp(key, "seg_num")) {

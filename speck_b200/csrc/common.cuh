@@ -117,6 +117,9 @@ void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trai
 // exclusive scan of in[0..n-1) into 64-bit out[0..n) (out[n-1] = total, also stored in sc->mapTotal)
 void launch_scan_map(const LaunchCtx &lc, const u32 *in, u64 *out, u32 n, u64 *tileState, Scalars *sc);
 
+// device scalars -> mapped pinned host mirror + sequence word (polled by the host)
+void launch_publish(const LaunchCtx &lc, const Scalars *dSc, Scalars *hSc, volatile u32 *hSeq, u32 seq);
+
 // multi-GPU helpers: product-balanced row cuts from the u64 prefix of rowOps (prefix[rows] = P); row_offsets of a
 // slab shifted by the slab's first position in the concatenated C
 void launch_find_cuts(const LaunchCtx &lc, const u64 *prefix, u32 rows, u32 parts, u32 *cuts, u64 *partProducts);
@@ -187,7 +190,10 @@ template <typename T>
 void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
                           const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
                           u32 colsB, const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, const u32 *cRp,
-                          u32 *cCi, T *cV);
+                          u32 *cCi, T *cV,
+                          int seq = 0 /* local rows, sequential-k kernel (dense_seq.cuh): 1 = lane loads, 2 = TMA-staged B segments */,
+                          const u32 *rowOps = nullptr /* products per row: the sequential-k kernel takes the rows that fold */);
+constexpr int DENSE_SEQ_MAX = 2048;   // distinct columns of a row the sequential-k kernel accumulates in shared memory
 
 template <typename T>
 void launch_compare(const LaunchCtx &lc, u32 rows, const u32 *rpA, const u32 *ciA, const T *vA, const u32 *rpB,

@@ -15,6 +15,7 @@
 //     value window, no shared-memory CAS loops and no separate sorting pass are needed.
 // Rows are pulled from a device-side queue (atomic counter), CTAs are persistent.
 #include "common.cuh"
+#include "dense_seq.cuh"
 
 namespace sb {
 
@@ -86,7 +87,7 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
              const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
              const u32 *__restrict__ bCi, const T *__restrict__ bV, const int winBits,
              const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax, u32 *bitmapStore, u32 *cRp,
-             u32 *__restrict__ cCi, T *cV)
+             u32 *__restrict__ cCi, T *cV, const u32 seqMax, const u32 *__restrict__ rowOps)
 {
     extern __shared__ __align__(16) u32 dsm[];
     const u32 W = 1u << winBits;
@@ -163,6 +164,7 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
         const u32 ri = sRow;
         if (ri >= count) break;
         const u32 row = perm[ri];
+        if (NUMERIC && seqMax && dense_seq_takes(rowOps[row], cRp[row + 1] - cRp[row], seqMax)) continue;   // k_dense_seq's row
         const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
         const bool oneBatch = (aEnd - aBeg) <= (u32)THREADS;
         const u32 colMin = rowMin[row], colMax = rowMax[row];
@@ -330,7 +332,8 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
 template <int THREADS, typename T, bool NUMERIC, int SVALS>
 static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u32 count, u32 *rowCounter,
                            const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
-                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *cRp, u32 *cCi, T *cV)
+                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *cRp, u32 *cCi, T *cV,
+                           u32 seqMax = 0, const u32 *rowOps = nullptr)
 {
     const size_t smem = dense_smem_bytes(winBits, THREADS, sizeof(T)) + (size_t)SVALS * sizeof(T);
     auto kern = k_dense_rows<THREADS, T, NUMERIC, SVALS>;
@@ -341,7 +344,7 @@ static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u3
     u32 grid = (u32)(lc.smCount * perSm);
     if (grid > count) grid = count;
     kern<<<grid, THREADS, smem, lc.stream>>>(perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, winBits, rowMin,
-                                             rowMax, bitmapStore, cRp, cCi, cV);
+                                             rowMax, bitmapStore, cRp, cCi, cV, seqMax, rowOps);
     ++*lc.launches;
 }
 
@@ -370,22 +373,33 @@ template <typename T>
 void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
                           const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
                           u32 colsB, const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, const u32 *cRp,
-                          u32 *cCi, T *cV)
+                          u32 *cCi, T *cV, int seq, const u32 *rowOps)
 {
     if (count == 0) return;
     u32 *rp = const_cast<u32 *>(cRp);
+    // sequential-k kernel with TMA-staged B segments (dense_seq.cuh): local rows with a kept bitmap whose distinct
+    // columns fit its shared accumulator; bulk copies need 16-byte aligned B arrays
+    const bool tma = seq == 2 && ((reinterpret_cast<uintptr_t>(bCi) | reinterpret_cast<uintptr_t>(bV)) & 15u) == 0;
+    const bool useSeq = seq && local && bitmapStore && rowOps;
+    if (useSeq && tma) {
+        launch_dense_seq_t<T, 512, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 0u, rowOps);
+        launch_dense_seq_t<T, DENSE_SEQ_MAX, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 512u, rowOps);
+    } else if (useSeq) {
+        launch_dense_seq_t<T, 512, false>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 0u, rowOps);
+        launch_dense_seq_t<T, DENSE_SEQ_MAX, false>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 512u, rowOps);
+    }
     if (local)
         launch_dense_t<256, T, true, 2048>(lc, DENSE_LOCAL_BITS, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV,
-                                           rowMin, rowMax, bitmapStore, rp, cCi, cV);
+                                           rowMin, rowMax, bitmapStore, rp, cCi, cV, useSeq ? (u32)DENSE_SEQ_MAX : 0u, rowOps);
     else
         launch_dense_t<1024, T, true, 4096>(lc, dense_window_bits(colsB), perm, count, rowCounter, aRp, aCi, aV, bRp,
                                             bCi, bV, rowMin, rowMax, nullptr, rp, cCi, cV);
 }
 template void launch_dense_numeric<double>(const LaunchCtx &, bool, const u32 *, u32, u32 *, const u32 *, const u32 *,
                                            const double *, const u32 *, const u32 *, const double *, u32,
-                                           const u32 *, const u32 *, u32 *, const u32 *, u32 *, double *);
+                                           const u32 *, const u32 *, u32 *, const u32 *, u32 *, double *, int, const u32 *);
 template void launch_dense_numeric<float>(const LaunchCtx &, bool, const u32 *, u32, u32 *, const u32 *, const u32 *,
                                           const float *, const u32 *, const u32 *, const float *, u32,
-                                          const u32 *, const u32 *, u32 *, const u32 *, u32 *, float *);
+                                          const u32 *, const u32 *, u32 *, const u32 *, u32 *, float *, int, const u32 *);
 
 }  // namespace sb

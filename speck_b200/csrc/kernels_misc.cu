@@ -369,6 +369,27 @@ void launch_scan_map(const LaunchCtx &lc, const u32 *in, u64 *out, u32 n, u64 *t
 }
 
 // ------------------------------------------------------------------------------------------
+// Scalars -> mapped pinned host memory, then a sequence number: the host polls the sequence word instead of going
+// through cudaStreamSynchronize (the two mid-pipeline read-backs of one multiply: bin counts, nnz(C)).  Replaces
+// the reference's blocking 4/8-byte cudaMemcpy's (source/GPU/Multiply.cu:250, 573, 615).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_publish(const Scalars *__restrict__ dSc, Scalars *hSc, volatile u32 *hSeq, u32 seq)
+{
+    const u32 *src = reinterpret_cast<const u32 *>(dSc);
+    volatile u32 *dst = reinterpret_cast<volatile u32 *>(hSc);
+    for (u32 i = threadIdx.x; i < sizeof(Scalars) / 4; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *hSeq = seq;
+}
+
+void launch_publish(const LaunchCtx &lc, const Scalars *dSc, Scalars *hSc, volatile u32 *hSeq, u32 seq)
+{
+    k_publish<<<1, 128, 0, lc.stream>>>(dSc, hSc, hSeq, seq);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------
 // Multi-GPU helpers (no reference counterpart: the reference is single-device).
 //   k_find_cuts:   contiguous row cuts balanced by products: cut g = first row whose exclusive product prefix
 //                  reaches g * P / parts (prefix = the u64 scan of rowOps), cuts[0] = 0, cuts[parts] = rows

@@ -26,9 +26,9 @@ def test_uniform_random(ctx, n, d, seed):
     check_case(ctx, M.uniform_random(n, n, d, seed), what=f"uniform {n} {d}")
 
 
-@pytest.fixture(params=[(16384, 1, 1, 1, 8, 0), (16384, 1, 1, 1, 16, 1), (16384, 1, 1, 0, 8, 0), (8192, 1, 0, 1, 8, 0),
-                        (8192, 0, 1, 1, 8, 0), (8192, 0, 0, 1, 8, 0), (1024, 1, 1, 1, 8, 1), (64, 1, 1, 1, 8, 0),
-                        (64, 1, 0, 1, 8, 0)],
+@pytest.fixture(params=[(16384, 1, 1, 1, 8, 0, 1), (16384, 1, 1, 1, 16, 1, 2), (16384, 1, 1, 0, 8, 0, 0), (8192, 1, 0, 1, 8, 0, 1),
+                        (8192, 0, 1, 1, 8, 0, 0), (8192, 0, 0, 1, 8, 0, 1), (1024, 1, 1, 1, 8, 1, 1), (64, 1, 1, 1, 8, 0, 1),
+                        (64, 1, 0, 1, 8, 0, 0)],
                 ids=["16384-flat8-map", "16384-flat16-seg-map", "16384-rank-map", "8192-rank", "8192-sort-map", "8192-sort",
                      "1024-seg-map", "64-map", "64"])
 def sort_max(ctx, request):
@@ -42,6 +42,7 @@ def sort_max(ctx, request):
     ctx.set_option("flat_sym", request.param[3])
     ctx.set_option("flat_e", request.param[4])
     ctx.set_option("seg_num", request.param[5])
+    ctx.set_option("dense_seq", request.param[6])
     yield request.param[0]
     ctx.set_option("sort_max", 16384)
     ctx.set_option("rank_path", 1)
@@ -49,6 +50,7 @@ def sort_max(ctx, request):
     ctx.set_option("flat_sym", 1)
     ctx.set_option("flat_e", 8)
     ctx.set_option("seg_num", 0)
+    ctx.set_option("dense_seq", 1)
 
 
 @pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16), (15, 16)])
@@ -205,6 +207,42 @@ def test_fem_like_high_compression(ctx):
     got, st = check_case(ctx, A, what="fem3d")
     assert st["class_rows"]["dense_local"] > 0
     assert st["products"] > 8 * st["nnz_c"]
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["lane-loads", "tma-staged"])
+def test_dense_seq_rows_are_bit_equal_to_the_oracle(ctx, variant):
+    """The sequential-k kernel (dense_seq.cuh) adds the products of an entry of C in ascending k with separately
+    rounded products -- the oracle's order: rows it handles are bit-identical to the oracle and run-to-run."""
+    ctx.set_option("dense_seq", variant)
+    A = M.fem3d_like(9, 8, 7)
+    first, st = gpu_multiply(ctx, A)
+    assert st["class_rows"]["dense_local"] == A.rows     # every row takes the bitmap path with a kept bitmap
+    want = oracle_multiply(A, A)
+    np.testing.assert_array_equal(first.col_ids, want.col_ids)
+
+    def seq_mask(Mx, Cx):
+        """entries of C in rows the sequential-k kernel takes: <= 2048 entries, >= 6 products per entry"""
+        import oracle
+        ops = oracle.row_products(Mx.row_offsets, Mx.col_ids, Mx.row_offsets)[0].astype(np.int64)
+        nnz = np.diff(Cx.row_offsets.astype(np.int64))
+        return np.repeat((nnz <= 2048) & (ops >= 6 * nnz), nnz)
+    m = seq_mask(A, want)
+    assert m.mean() > 0.9
+    np.testing.assert_array_equal(first.data[m], want.data[m])  # bit-exact, not just 1e-6
+    np.testing.assert_allclose(first.data, want.data, rtol=1e-6)
+    again, _ = gpu_multiply(ctx, A)
+    np.testing.assert_array_equal(again.data[m], first.data[m])
+    # long B rows (several 128-entry pieces per segment) and B rows of every alignment
+    B = M.banded_fem_like(n=3000, per_row=300, clusters=3, band=600, seed=5)
+    got, st = gpu_multiply(ctx, B)
+    assert ndense(st) > 0
+    wantB = oracle_multiply(B, B)
+    np.testing.assert_array_equal(got.col_ids, wantB.col_ids)
+    mask = seq_mask(B, wantB)
+    assert mask.any()
+    np.testing.assert_array_equal(got.data[mask], wantB.data[mask])
+    np.testing.assert_allclose(got.data, wantB.data, rtol=1e-6)
+    ctx.set_option("dense_seq", 1)
 
 
 def test_dense_rows_exceeding_shared_accumulator(ctx):
