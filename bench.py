@@ -310,6 +310,8 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference spECK CUDA build (oracle/_ref) on the same GPU")
     ap.add_argument("--no-sweep", action="store_true", help="N = 1: skip the sweep over the other BASELINE configs")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling figure")
+    ap.add_argument("--part-row-cost", type=int, default=8, help="N > 1: cost of a row in products for the partition")
+    ap.add_argument("--part-entry-cost", type=int, default=2, help="N > 1: cost of an entry of A in products for the partition")
     ap.add_argument("--sort-max", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     args = ap.parse_args()
@@ -399,9 +401,14 @@ def main():
         # product-balanced cuts from the device analysis on rank 0, then 4*(N+1) bytes to every rank
         t_cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
         if rank == 0:
+            # a row costs about as much as 7 products, an entry of A about 1.5 (measured on this matrix): balance that,
+            # not the products alone (pure product cuts give the ranks with the many tiny rows 30 % more time)
+            ctx.set_option("partition_row_cost", args.part_row_cost)
+            ctx.set_option("partition_entry_cost", args.part_entry_cost)
             c32, part_products = ctx.partition_rows(dB, dB, world)
             t_cuts = torch.from_numpy(c32.astype(np.int64)).to(dev)
-            extra["partition"] = {"cuts": [int(x) for x in c32], "products_per_rank": [int(x) for x in part_products]}
+            extra["partition"] = {"cuts": [int(x) for x in c32], "balanced_cost_per_rank": [int(x) for x in part_products],
+                                  "cost_model": f"products + {args.part_entry_cost} * nnz(A row) + {args.part_row_cost} per row"}
         dist.broadcast(t_cuts, 0)
         cuts = t_cuts.cpu().numpy()
         slab = A.row_slice(int(cuts[rank]), int(cuts[rank + 1]))

@@ -170,7 +170,7 @@ void *speck_b200_stream(speck_ctx *ctx);
 
 /* Row cuts of A balanced by products, computed on the device: analysis (row products) -> 64-bit scan -> search.
  * cuts: host array of parts + 1 row indices (cuts[0] = 0, cuts[parts] = A->rows); part_products (may be NULL):
- * host array of parts product counts.  A and B are device views on ctx's device. */
+ * host array of parts product counts (of the balanced cost when the partition_*_cost options are set).  A and B are device views on ctx's device. */
 int speck_b200_partition_rows(speck_ctx *ctx, const speck_csr *A, const speck_csr *B, int parts, uint32_t *cuts,
                               uint64_t *part_products);
 
@@ -214,6 +214,19 @@ int speck_b200_sharded_destroy(speck_shard_plan *plan);
  *                       0: self-contained numeric kernels
  *   "sym_streams", "num_streams"   side streams of the two phases (1..4; num_streams 0 = automatic)
  *   "map_min_class", "map_cta_min" which lane-group classes use the rank map / the CTA map kernel
+ *   "flat_sym"          1 (default): mapped two-level symbolic kernel = flat variant with cp.async-staged columns
+ *                       (rank_flat.cuh), 0: register-slot variant (rank_cta.cuh); "flat_e" 8 / 16 slots per thread
+ *   "dense_seq"         banded / high-compression rows: 1 (default) sequential-k numeric kernel with lane loads,
+ *                       2: the same with TMA (cp.async.bulk) staged B segments, 0: product-parallel kernel only
+ *   "deterministic"     1: values bit-reproducible and in the CPU oracle's summation order (ascending k, products
+ *                       rounded before they are added); slower: no rank map, sort classes, rows that accumulate
+ *                       with atomics are recomputed.  Default 0 (like the reference: "not bit stable")
+ *   "spin_wait"         1 (default): the two mid-pipeline scalar read-backs poll mapped pinned memory, 0: they use
+ *                       cudaMemcpyAsync + cudaStreamSynchronize
+ *   "partition_row_cost", "partition_entry_cost"   speck_b200_partition_rows balances products + entry_cost * nnz(A row)
+ *                       + row_cost per row instead of products alone (default 0, 0).  Measured on the config-5
+ *                       matrix: a row costs about as much as 7 products, an entry of A about 1.5 (profiles/r2_notes.md)
+ *   "seg_num", "hash_count"        experiments kept for the record (profiles/r2_notes.md), off by default
  *   "release_workspace" 1 frees the pooled workspace now. */
 int speck_b200_set_option(speck_ctx *ctx, const char *key, long long value);
 

@@ -12,7 +12,7 @@ from speck_b200 import api  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="rmat20")
-ap.add_argument("--seed", type=int, default=20)
+ap.add_argument("--seed", type=int, default=None)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--opt", action="append", default=[])
 a = ap.parse_args()

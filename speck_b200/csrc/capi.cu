@@ -83,6 +83,10 @@ struct speck_ctx {
     size_t rankMapMaxBytes = ~(size_t)0;  // test hook: larger maps are treated as "does not fit" (exercises the fallbacks)
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
+    u32 partRowCost = 0, partEntryCost = 0;   // partition_rows: cost of a row = products + partEntryCost * entries + partRowCost
+    bool deterministic = false;   // bit-reproducible values in the oracle's summation order (slower): sort classes
+                              // up to 8192 products, sequential-k kernel for every local bitmap row that fits, the
+                              // remaining bitmap rows recomputed by k_det_rows
     int denseSeq = 1;         // banded / high-compression rows: sequential-k numeric kernel (dense_seq.cuh): 0 = off,
                               // 1 = B segments loaded by the lanes, 2 = staged by TMA bulk copies
     int segNum = 0;           // mapped numeric CTA classes: 1 = segment-major kernel (map_seg.cuh; measured slower: fewer
@@ -198,10 +202,11 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // CTA-level sort classes (> 1024 products) are used only while (col << log2 N) fits a u32 key;
     // wider matrices send those rows to the bitmap path instead of sorting u64 keys.
     u32 sortMax = c->sortMax;
-    const bool wantMap = c->rankMapOn;
+    const bool det = c->deterministic;
+    const bool wantMap = c->rankMapOn && !det;   // mapped numeric kernels add repeated columns with shared atomics
     // rank classes (no key-width limit): two bitmap levels up to 2^20 columns, three up to 2^25 (mapped only)
     const int rankLevels = colsB <= RANK_EXTENT_LIMIT ? 2 : 3;
-    const bool useRank = c->rankPath && (rankLevels == 2 || (colsB <= RANK_EXTENT_LIMIT3 && wantMap));
+    const bool useRank = !det && c->rankPath && (rankLevels == 2 || (colsB <= RANK_EXTENT_LIMIT3 && wantMap));
     if (!(useRank && wantMap) && sortMax > SORT_MAX_PRODUCTS) sortMax = SORT_MAX_PRODUCTS;  // 8193..16384: mapped rank kernels only
     if (sortMax > 1024 && !useRank) {  // largest power-of-two network whose keys fit 32 bits: cols * N <= 2^32
         u32 fit = 8192;
@@ -241,10 +246,11 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     launch_row_info(lc, (u32)B->rows, bRp, bCi, (uint4 *)c->rowInfo.p);
     launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
                    wantMap ? (uint2 *)c->aSeg.p : nullptr, (const uint4 *)c->rowInfo.p,
-                   wantMap && c->segNum ? (u32 *)c->aOff.p : nullptr);
-    launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (u32 *)c->mapLen.p : nullptr,
-                       useRank, c->mapMinClass);
+                   wantMap && c->segNum ? (u32 *)c->aOff.p : nullptr, wantMap ? (u32 *)c->mapLen.p : nullptr, useRank,
+                   c->mapMinClass);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
+    launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (const u64 *)c->mapBase.p : nullptr,
+                       wantMap ? (RowDesc *)c->desc.p : nullptr);
     cudaEventRecord(c->evStage[1], c->main);
     if ((rc = read_scalars(c, lc))) return rc;
     const Scalars s1 = *c->hSc;
@@ -289,8 +295,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             rankMap = (unsigned short *)c->rankMap.p;
             desc = (RowDesc *)c->desc.p;
             aSeg = (const uint2 *)c->aSeg.p;
-            // descriptors of all binned rows, perm order (desc + binStart[b] = first row of bin b)
-            launch_build_desc(lc, perm, binStart[NUM_BINS], aRp, rowOps, rowMin, rowMax, (const u64 *)c->mapBase.p, desc);
+            // descriptors of all binned rows are in place, perm order (desc + binStart[b] = first row of bin b)
         }
     }
     // ---- symbolic: dense rows first (longest), then the sort classes from large to small
@@ -301,7 +306,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (!s1.binCount[bin]) continue;
         LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         launch_dense_symbolic(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[loc], aRp,
-                              aCi, bRp, bCi, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp);
+                              aCi, bRp, bCi, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp,
+                              rowOps, (loc && (c->denseSeq || det)) ? c->dSc->seqRows : nullptr, det);
     }
     // rank classes: the CTA sort bins grouped by launch shape (products <= 8192 / 4096 / 2048 / 1024)
     if (useRank) {
@@ -348,6 +354,8 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     if ((rc = read_scalars(c, lc))) return rc;
     CU_TRY(cudaGetLastError());
     const u64 nnzC = c->hSc->nnzC;
+    const int seqKind = c->denseSeq ? c->denseSeq : (det ? 1 : 0);
+    const int denseSeq = seqKind ? (seqKind | (c->hSc->seqRows[0] ? 4 : 0) | (c->hSc->seqRows[1] ? 8 : 0) | (det ? 16 : 0)) : 0;
     if (nnzC > 0xffffffffull) return fail(SPECK_ERR_OVERFLOW, "nnz(C) = %llu does not fit the u32 row_offsets of the spECK API", (unsigned long long)nnzC);
 
     // ---- alloc C (Multiply.cu:589-602): only when nnz changed
@@ -382,7 +390,10 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         LaunchCtx ls{c->side[NSIDE - 1], c->smCount, &c->launches};
         launch_dense_numeric<T>(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[2 + loc],
                                 aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV,
-                                c->denseSeq, rowOps);
+                                denseSeq, rowOps);
+        if (det)   // same stream: the bitmap kernel has written the row's columns
+            launch_det_rows<T>(ls, perm + binStart[bin], s1.binCount[bin], aRp, aCi, aV, bRp, bCi, bV, cRp, cCi, cV, rowOps,
+                               loc && bitmapStore && (denseSeq & 12));
     }
     if (useRank) {
         for (int g = RANK_GROUPS - 1; g >= 0; --g) {
@@ -828,6 +839,7 @@ int speck_b200_partition_rows(speck_ctx *c, const speck_csr *A, const speck_csr 
     LaunchCtx lc{c->main, c->smCount, &n};
     launch_analyze(lc, rows, A->nnz, A->row_offsets, A->col_ids, B->row_offsets, B->col_ids, (u32 *)c->rowOps.p,
                    (u32 *)c->rowMin.p, (u32 *)c->rowMax.p, (u32 *)c->perm.p, c->dSc, c->sortMax, nullptr, nullptr);
+    launch_row_cost(lc, rows, A->row_offsets, (u32 *)c->rowOps.p, c->partRowCost, c->partEntryCost);
     u64 *prefix = (u64 *)c->mapBase.p;
     launch_scan_map(lc, (const u32 *)c->rowOps.p, prefix, rows + 1, (u64 *)c->tileState.p, c->dSc);
     u64 *dPart = prefix + rows + 1;
@@ -1139,6 +1151,15 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     }
     if (!strcmp(key, "rank_map")) {
         c->rankMapOn = value != 0;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "partition_row_cost") || !strcmp(key, "partition_entry_cost")) {
+        if (value < 0 || value > 1024) return fail(SPECK_ERR_INVALID, "%s must be in [0, 1024]", key);
+        (key[10] == 'r' ? c->partRowCost : c->partEntryCost) = (u32)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "deterministic")) {
+        c->deterministic = value != 0;
         return SPECK_OK;
     }
     if (!strcmp(key, "dense_seq")) {

@@ -50,6 +50,8 @@ struct Scalars {
     u32 tileCounter;          // dynamic tile ids of the row_ptr scan
     u32 mapTileCounter;       // dynamic tile ids of the rank-map offset scan
     u64 mapTotal;             // entries of the rank map (products of all mapped rows)
+    u32 seqRows[2];           // local bitmap rows the sequential-k numeric kernel takes (<= 512 / <= 2048 entries), counted
+                              // by the symbolic kernel so that the host launches those kernels only when needed
     u32 compareFlag;          // k_compare: 0 = equal
     u64 compareFirst;         // k_compare: smallest (row << 32 | kind << 28 | position in row) that differs; kind 0 = row
                               // length, 1 = column id, 2 = value (first-mismatch report)
@@ -100,18 +102,19 @@ struct LaunchCtx {
 // kernels need one load level (aSeg) instead of two (A.col_ids -> B.row_offsets)
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff = nullptr);
+                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff = nullptr, u32 *mapLen = nullptr, bool mapCta = false,
+                    int mapMinClass = 0);
 // rowInfo[k] = (begin, end, first column, last column) of B row k: one gather per A entry in the analysis
 void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *bCi, uint4 *rowInfo);
-// descriptors of perm[0..count): symbolic flavour (c0/c1 = column extent), then switched to the numeric
+// descriptors (written by launch_bin_scatter, symbolic flavour: c0/c1 = column extent) switched to the numeric
 // flavour (c0/c1 = position / length in C) once row_offsets are scanned
-void launch_build_desc(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *rowOps,
-                       const u32 *rowMin, const u32 *rowMax, const u64 *mapBase, RowDesc *desc);
 void launch_desc_numeric(const LaunchCtx &lc, u32 count, const u32 *cRp, RowDesc *desc);
-// mapLen (optional, rows + 1 entries): products of the row when its class records a rank map in the symbolic
-// phase (lane-group classes from mapMinClass on, CTA classes when mapCta), else 0
+// mapLen (launch_analyze; optional, rows + 1 entries): products of the row when its class records a rank map in
+// the symbolic phase (lane-group classes from mapMinClass on, CTA classes when mapCta), else 0.
+// launch_bin_scatter: one permutation ordered by bin and, when desc != nullptr, the row descriptors in that order
+// (mapBase = exclusive scan of mapLen)
 void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
-                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta, int mapMinClass);
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, const u64 *mapBase, RowDesc *desc);
 void launch_scan(const LaunchCtx &lc, u32 *data, u32 n /* entries incl. the trailing total slot */,
                  u64 *tileState, Scalars *sc);
 // exclusive scan of in[0..n-1) into 64-bit out[0..n) (out[n-1] = total, also stored in sc->mapTotal)
@@ -122,6 +125,7 @@ void launch_publish(const LaunchCtx &lc, const Scalars *dSc, Scalars *hSc, volat
 
 // multi-GPU helpers: product-balanced row cuts from the u64 prefix of rowOps (prefix[rows] = P); row_offsets of a
 // slab shifted by the slab's first position in the concatenated C
+void launch_row_cost(const LaunchCtx &lc, u32 rows, const u32 *aRp, u32 *rowOps, u32 wRow, u32 wEntry);
 void launch_find_cuts(const LaunchCtx &lc, const u64 *prefix, u32 rows, u32 parts, u32 *cuts, u64 *partProducts);
 void launch_offset_rows(const LaunchCtx &lc, const u32 *in, u32 n, u32 base, u32 *out);
 
@@ -184,15 +188,25 @@ void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, 
 int dense_window_bits(u64 colsB);
 void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
                            const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB,
-                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz);
+                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz,
+                           const u32 *rowOps = nullptr, u32 *seqRows = nullptr /* Scalars::seqRows, counted for local rows */,
+                           bool everyRow = false /* deterministic mode: count every row that fits, whatever its fold */);
 size_t dense_local_store_bytes(u32 count);
 template <typename T>
 void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
                           const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
                           u32 colsB, const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, const u32 *cRp,
                           u32 *cCi, T *cV,
-                          int seq = 0 /* local rows, sequential-k kernel (dense_seq.cuh): 1 = lane loads, 2 = TMA-staged B segments */,
+                          int seq = 0 /* local rows, sequential-k kernel (dense_seq.cuh): 1 = lane loads, 2 = TMA-staged B segments;
+                                         +4: rows of <= 512 entries exist, +8: rows of 513..2048 entries exist,
+                                         +16: deterministic mode (every row that fits the accumulator) */,
                           const u32 *rowOps = nullptr /* products per row: the sequential-k kernel takes the rows that fold */);
+// deterministic mode: values of the rows of a bitmap bin recomputed in the oracle's order (dense_seq.cuh: k_det_rows);
+// skipSeqRows: rows the sequential-k kernel wrote are left alone
+template <typename T>
+void launch_det_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi, const T *aV,
+                     const u32 *bRp, const u32 *bCi, const T *bV, const u32 *cRp, const u32 *cCi, T *cV,
+                     const u32 *rowOps, bool skipSeqRows);
 constexpr int DENSE_SEQ_MAX = 2048;   // distinct columns of a row the sequential-k kernel accumulates in shared memory
 
 template <typename T>

@@ -65,10 +65,10 @@ template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { r
 // fold into every entry of C on average.  Measured (profiles/r2_notes.md): at 17.7 products per entry (cant-like)
 // it runs 1.4x faster than the product-parallel kernel, whose shared fp64 atomics then contend; at 2.2 (banded
 // generator) it is 1.4x slower (short B rows leave most lanes of a step idle).
-constexpr u32 DENSE_SEQ_FOLD = 6;
-__host__ __device__ __forceinline__ bool dense_seq_takes(u32 products, u32 nnzRow, u32 seqMax)
+constexpr u32 DENSE_SEQ_FOLD = 6;   // fold = 0 (deterministic mode): every row that fits
+__host__ __device__ __forceinline__ bool dense_seq_takes(u32 products, u32 nnzRow, u32 seqMax, u32 fold)
 {
-    return nnzRow <= seqMax && (u64)products >= (u64)DENSE_SEQ_FOLD * nnzRow;
+    return nnzRow <= seqMax && (u64)products >= (u64)fold * nnzRow;
 }
 
 constexpr int SEQ_WORDS = 1 << (DENSE_LOCAL_BITS - 5);   // bitmap words of a local row (512)
@@ -102,7 +102,7 @@ k_dense_seq(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
             const T *__restrict__ aV, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi, const T *__restrict__ bV,
             const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax, const u32 *__restrict__ bitmapStore,
             const u32 *__restrict__ cRp, u32 *__restrict__ cCi, T *__restrict__ cV, const u32 minNnz,
-            const u32 *__restrict__ rowOps)
+            const u32 *__restrict__ rowOps, const u32 fold)
 {
     __shared__ DenseSeqSmem<T, SV, TMA> sm;
     const u32 lane = threadIdx.x;
@@ -111,7 +111,7 @@ k_dense_seq(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
     const u32 row = perm[ri];
     const u32 cBase = cRp[row], nnzRow = cRp[row + 1] - cBase;
     // another shape of this kernel, or k_dense_rows, takes the row (same test there: dense_seq_takes)
-    if (nnzRow > (u32)SV || nnzRow <= minNnz || !dense_seq_takes(rowOps[row], nnzRow, (u32)DENSE_SEQ_MAX)) return;
+    if (nnzRow > (u32)SV || nnzRow <= minNnz || !dense_seq_takes(rowOps[row], nnzRow, (u32)DENSE_SEQ_MAX, fold)) return;
     const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
     const u32 base0 = rowMin[row] & ~127u;
     const u32 extWords = ((rowMax[row] - base0) >> 5) + 1;   // <= SEQ_WORDS for rows of this bin
@@ -273,9 +273,62 @@ k_dense_seq(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
 template <typename T, int SV, bool TMA>
 void launch_dense_seq_t(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi, const T *aV,
                         const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowMin, const u32 *rowMax,
-                        const u32 *bitmapStore, const u32 *cRp, u32 *cCi, T *cV, u32 minNnz, const u32 *rowOps)
+                        const u32 *bitmapStore, const u32 *cRp, u32 *cCi, T *cV, u32 minNnz, const u32 *rowOps, u32 fold)
 {
-    k_dense_seq<T, SV, TMA><<<count, 32, 0, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, minNnz, rowOps);
+    k_dense_seq<T, SV, TMA><<<count, 32, 0, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, minNnz, rowOps, fold);
+    ++*lc.launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic mode (option "deterministic"; the reference is "not bit stable", config.ini:8-9): values of the
+// rows whose numeric kernel accumulates with atomics (rows beyond the sort classes, wide bitmap rows) are
+// recomputed in the oracle's order.  The columns of the row are already in C (sorted); one CTA walks the A entries
+// in ascending k, the products of one B row go to distinct entries of C (found by binary search), so every step is
+// a plain read-modify-write; products are rounded before they are added.  Slow (a barrier per A entry), used
+// for the few rows no deterministic kernel takes.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_det_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp, const u32 *__restrict__ aCi,
+           const T *__restrict__ aV, const u32 *__restrict__ bRp, const u32 *__restrict__ bCi, const T *__restrict__ bV,
+           const u32 *__restrict__ cRp, const u32 *__restrict__ cCi, T *cV, const u32 *__restrict__ rowOps,
+           const u32 seqMax, const u32 fold)
+{
+    for (u32 ri = blockIdx.x; ri < count; ri += gridDim.x) {
+        const u32 row = perm[ri];
+        const u32 cBase = cRp[row], nnzRow = cRp[row + 1] - cBase;
+        if (seqMax && dense_seq_takes(rowOps[row], nnzRow, seqMax, fold)) continue;   // k_dense_seq wrote this row
+        volatile T *out = cV + cBase;
+        for (u32 j = threadIdx.x; j < nnzRow; j += 256) out[j] = (T)0;
+        __syncthreads();
+        const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
+        for (u32 e = aBeg; e < aEnd; ++e) {
+            const u32 k = __ldg(aCi + e);
+            const T av = __ldg(aV + e);
+            const u32 bs = __ldg(bRp + k), be = __ldg(bRp + k + 1);
+            for (u32 q = bs + threadIdx.x; q < be; q += 256) {
+                const u32 col = __ldg(bCi + q);
+                u32 lo = 0, hi = nnzRow;   // position of col in the row of C
+                while (lo < hi) {
+                    const u32 mid = (lo + hi) >> 1;
+                    if (__ldg(cCi + cBase + mid) < col) lo = mid + 1; else hi = mid;
+                }
+                out[lo] = add_rn<T>(out[lo], mul_rn<T>(av, __ldg(bV + q)));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename T>
+void launch_det_rows_t(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi, const T *aV,
+                       const u32 *bRp, const u32 *bCi, const T *bV, const u32 *cRp, const u32 *cCi, T *cV,
+                       const u32 *rowOps, u32 seqMax, u32 fold)
+{
+    if (count == 0) return;
+    u32 grid = (u32)lc.smCount * 8u;
+    if (grid > count) grid = count;
+    k_det_rows<T><<<grid, 256, 0, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, cRp, cCi, cV, rowOps, seqMax, fold);
     ++*lc.launches;
 }
 

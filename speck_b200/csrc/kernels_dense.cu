@@ -87,7 +87,7 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
              const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
              const u32 *__restrict__ bCi, const T *__restrict__ bV, const int winBits,
              const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax, u32 *bitmapStore, u32 *cRp,
-             u32 *__restrict__ cCi, T *cV, const u32 seqMax, const u32 *__restrict__ rowOps)
+             u32 *__restrict__ cCi, T *cV, const u32 seqMax, const u32 *__restrict__ rowOps, u32 *seqRows, const u32 fold)
 {
     extern __shared__ __align__(16) u32 dsm[];
     const u32 W = 1u << winBits;
@@ -164,7 +164,7 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
         const u32 ri = sRow;
         if (ri >= count) break;
         const u32 row = perm[ri];
-        if (NUMERIC && seqMax && dense_seq_takes(rowOps[row], cRp[row + 1] - cRp[row], seqMax)) continue;   // k_dense_seq's row
+        if (NUMERIC && seqMax && dense_seq_takes(rowOps[row], cRp[row + 1] - cRp[row], seqMax, fold)) continue;   // k_dense_seq's row
         const u32 aBeg = aRp[row], aEnd = aRp[row + 1];
         const bool oneBatch = (aEnd - aBeg) <= (u32)THREADS;
         const u32 colMin = rowMin[row], colMax = rowMax[row];
@@ -189,6 +189,8 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                 __syncthreads();
             } else {
                 // ---------------------------------------------- pass A: set column bits
+                // (a variant with 16 lanes per B row and no owner search was measured on the cant-shaped matrix: symbolic
+                // 0.86 -> 1.01 ms -- consecutive columns of a FEM cluster hit the same bitmap word and the atomics serialise)
                 for (u32 ab = aBeg; ab < aEnd; ab += THREADS) {
                     total = load_batch(ab, aEnd, trim, winLo, winHi, nb);
                     // four products per thread and iteration: the four column loads are in flight together
@@ -325,7 +327,10 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
             __syncthreads();
             winBase += winTotal;
         }
-        if (!NUMERIC && tid == 0) cRp[row] = winBase;
+        if (!NUMERIC && tid == 0) {
+            cRp[row] = winBase;
+            if (seqRows && dense_seq_takes(rowOps[row], winBase, (u32)DENSE_SEQ_MAX, fold)) atomicAdd(&seqRows[winBase <= 512u ? 0 : 1], 1u);
+        }
     }
 }
 
@@ -333,7 +338,7 @@ template <int THREADS, typename T, bool NUMERIC, int SVALS>
 static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u32 count, u32 *rowCounter,
                            const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
                            const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *cRp, u32 *cCi, T *cV,
-                           u32 seqMax = 0, const u32 *rowOps = nullptr)
+                           u32 seqMax = 0, const u32 *rowOps = nullptr, u32 *seqRows = nullptr, u32 fold = DENSE_SEQ_FOLD)
 {
     const size_t smem = dense_smem_bytes(winBits, THREADS, sizeof(T)) + (size_t)SVALS * sizeof(T);
     auto kern = k_dense_rows<THREADS, T, NUMERIC, SVALS>;
@@ -344,7 +349,7 @@ static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u3
     u32 grid = (u32)(lc.smCount * perSm);
     if (grid > count) grid = count;
     kern<<<grid, THREADS, smem, lc.stream>>>(perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, winBits, rowMin,
-                                             rowMax, bitmapStore, cRp, cCi, cV, seqMax, rowOps);
+                                             rowMax, bitmapStore, cRp, cCi, cV, seqMax, rowOps, seqRows, fold);
     ++*lc.launches;
 }
 
@@ -357,16 +362,19 @@ size_t dense_local_store_bytes(u32 count) { return (size_t)count * ((size_t)1 <<
 
 void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
                            const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB,
-                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz)
+                           const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz, const u32 *rowOps,
+                           u32 *seqRows, bool everyRow)
 {
     if (count == 0) return;
     const float *nv = nullptr;
     if (local)
         launch_dense_t<256, float, false, 0>(lc, DENSE_LOCAL_BITS, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv,
-                                             rowMin, rowMax, bitmapStore, rowNnz, nullptr, nullptr);
+                                             rowMin, rowMax, bitmapStore, rowNnz, nullptr, nullptr, 0u,
+                                             rowOps, (bitmapStore && rowOps) ? seqRows : nullptr,
+                                             everyRow ? 0u : DENSE_SEQ_FOLD);
     else
         launch_dense_t<1024, float, false, 0>(lc, dense_window_bits(colsB), perm, count, rowCounter, aRp, aCi, nv, bRp,
-                                              bCi, nv, rowMin, rowMax, nullptr, rowNnz, nullptr, nullptr);
+                                              bCi, nv, rowMin, rowMax, nullptr, rowNnz, nullptr, nullptr, 0u, rowOps);
 }
 
 template <typename T>
@@ -375,26 +383,43 @@ void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 
                           u32 colsB, const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, const u32 *cRp,
                           u32 *cCi, T *cV, int seq, const u32 *rowOps)
 {
+    const u32 fold = (seq & 16) ? 0u : DENSE_SEQ_FOLD;   // deterministic mode: every row that fits the accumulator
     if (count == 0) return;
     u32 *rp = const_cast<u32 *>(cRp);
     // sequential-k kernel with TMA-staged B segments (dense_seq.cuh): local rows with a kept bitmap whose distinct
     // columns fit its shared accumulator; bulk copies need 16-byte aligned B arrays
-    const bool tma = seq == 2 && ((reinterpret_cast<uintptr_t>(bCi) | reinterpret_cast<uintptr_t>(bV)) & 15u) == 0;
-    const bool useSeq = seq && local && bitmapStore && rowOps;
+    const bool tma = (seq & 3) == 2 && ((reinterpret_cast<uintptr_t>(bCi) | reinterpret_cast<uintptr_t>(bV)) & 15u) == 0;
+    const bool small = seq & 4, large = seq & 8;   // which shapes have rows (counted by the symbolic kernel)
+    const bool useSeq = (seq & 3) && (small || large) && local && bitmapStore && rowOps;
     if (useSeq && tma) {
-        launch_dense_seq_t<T, 512, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 0u, rowOps);
-        launch_dense_seq_t<T, DENSE_SEQ_MAX, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 512u, rowOps);
+        if (small) launch_dense_seq_t<T, 512, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 0u, rowOps, fold);
+        if (large) launch_dense_seq_t<T, DENSE_SEQ_MAX, true>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 512u, rowOps, fold);
     } else if (useSeq) {
-        launch_dense_seq_t<T, 512, false>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 0u, rowOps);
-        launch_dense_seq_t<T, DENSE_SEQ_MAX, false>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 512u, rowOps);
+        if (small) launch_dense_seq_t<T, 512, false>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 0u, rowOps, fold);
+        if (large) launch_dense_seq_t<T, DENSE_SEQ_MAX, false>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowMin, rowMax, bitmapStore, cRp, cCi, cV, 512u, rowOps, fold);
     }
     if (local)
         launch_dense_t<256, T, true, 2048>(lc, DENSE_LOCAL_BITS, perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV,
-                                           rowMin, rowMax, bitmapStore, rp, cCi, cV, useSeq ? (u32)DENSE_SEQ_MAX : 0u, rowOps);
+                                           rowMin, rowMax, bitmapStore, rp, cCi, cV, useSeq ? (u32)DENSE_SEQ_MAX : 0u, rowOps, nullptr, fold);
     else
         launch_dense_t<1024, T, true, 4096>(lc, dense_window_bits(colsB), perm, count, rowCounter, aRp, aCi, aV, bRp,
                                             bCi, bV, rowMin, rowMax, nullptr, rp, cCi, cV);
 }
+template <typename T>
+void launch_det_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi, const T *aV,
+                     const u32 *bRp, const u32 *bCi, const T *bV, const u32 *cRp, const u32 *cCi, T *cV,
+                     const u32 *rowOps, bool skipSeqRows)
+{
+    launch_det_rows_t<T>(lc, perm, count, aRp, aCi, aV, bRp, bCi, bV, cRp, cCi, cV, rowOps,
+                         skipSeqRows ? (u32)DENSE_SEQ_MAX : 0u, 0u);
+}
+template void launch_det_rows<double>(const LaunchCtx &, const u32 *, u32, const u32 *, const u32 *, const double *,
+                                      const u32 *, const u32 *, const double *, const u32 *, const u32 *, double *,
+                                      const u32 *, bool);
+template void launch_det_rows<float>(const LaunchCtx &, const u32 *, u32, const u32 *, const u32 *, const float *,
+                                     const u32 *, const u32 *, const float *, const u32 *, const u32 *, float *,
+                                     const u32 *, bool);
+
 template void launch_dense_numeric<double>(const LaunchCtx &, bool, const u32 *, u32, u32 *, const u32 *, const u32 *,
                                            const double *, const u32 *, const u32 *, const double *, u32,
                                            const u32 *, const u32 *, u32 *, const u32 *, u32 *, double *, int, const u32 *);

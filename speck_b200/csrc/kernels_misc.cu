@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                                                  u32 *__restrict__ rowOps, u32 *__restrict__ rowMin,
                                                  u32 *__restrict__ rowMax, u32 *__restrict__ rowNnz, Scalars *sc,
                                                  u32 sortMax, uint2 *__restrict__ aSeg,
-                                                 const uint4 *__restrict__ rowInfo, u32 *__restrict__ aOff)
+                                                 const uint4 *__restrict__ rowInfo, u32 *__restrict__ aOff,
+                                                 u32 *__restrict__ mapLen, bool mapCta, int mapMinClass)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -61,28 +62,49 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                                         // reference's rowColMinMax, common.cuh:395-400)
     const u32 beg = row < rows ? aRp[row] : 0u, end = row < rows ? aRp[row + 1] : 0u;
     aLen = end - beg;
-    // all LA lanes of the group run the same number of iterations (the per-entry product offsets need a group scan)
-    const u32 gmask = LA == 32 ? 0xffffffffu : (((1u << (LA & 31)) - 1u) << ((threadIdx.x & 31) - lane));
-    for (u32 p0 = beg; p0 < end; p0 += LA) {
-        const u32 p = p0 + lane;
-        u32 len = 0, bs = 0, be = 0;
-        if (p < end) {
-            const u32 k = __ldg(aCi + p);
-            if (rowInfo) {
-                const uint4 ri = __ldg(rowInfo + k);
-                bs = ri.x; be = ri.y;
-                cmin = min(cmin, ri.z);   // empty rows carry (0xffffffff, 0)
-                cmax = max(cmax, ri.w);
-            } else {
-                bs = __ldg(bRp + k); be = __ldg(bRp + k + 1);
-                if (be > bs) {
-                    cmin = min(cmin, __ldg(bCi + bs));
-                    cmax = max(cmax, __ldg(bCi + be - 1));
-                }
-            }
-            len = be - bs;
+    // B-row summary of one A entry: (begin, end, first column, last column); empty rows carry (0xffffffff, 0)
+    auto fetch = [&](u32 k) -> uint4 {
+        if (rowInfo) return __ldg(rowInfo + k);
+        uint4 ri = make_uint4(__ldg(bRp + k), __ldg(bRp + k + 1), 0xffffffffu, 0u);
+        if (ri.y > ri.x) {
+            ri.z = __ldg(bCi + ri.x);
+            ri.w = __ldg(bCi + ri.y - 1);
         }
-        if (aOff) {   // index of the entry's first product in the row's flat enumeration (u32: rows beyond 2^32 products are not mapped)
+        return ri;
+    };
+    const u32 gmask = LA == 32 ? 0xffffffffu : (((1u << (LA & 31)) - 1u) << ((threadIdx.x & 31) - lane));
+    if (!aOff) {
+        // four entries per lane and iteration: their summary gathers are in flight together (a hub row of A
+        // otherwise serialises hundreds of dependent column -> summary loads on one lane group)
+        for (u32 p0 = beg + lane; p0 < end; p0 += 4 * LA) {
+            u32 kk[4];
+            uint4 ri[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = (p0 + u * LA < end) ? __ldg(aCi + p0 + u * LA) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ri[u] = kk[u] != 0xffffffffu ? fetch(kk[u]) : make_uint4(0u, 0u, 0xffffffffu, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kk[u] == 0xffffffffu) continue;
+                cmin = min(cmin, ri[u].z);
+                cmax = max(cmax, ri[u].w);
+                ops64 += (u64)(ri[u].y - ri[u].x);
+                if (aSeg) aSeg[p0 + u * LA] = make_uint2(ri[u].x, ri[u].y);
+            }
+        }
+    } else {
+        // all LA lanes of the group run the same number of iterations (the per-entry product offsets need a group scan)
+        for (u32 p0 = beg; p0 < end; p0 += LA) {
+            const u32 p = p0 + lane;
+            u32 len = 0, bs = 0, be = 0;
+            if (p < end) {
+                const uint4 ri = fetch(__ldg(aCi + p));
+                bs = ri.x; be = ri.y;
+                cmin = min(cmin, ri.z);
+                cmax = max(cmax, ri.w);
+                len = be - bs;
+            }
+            // index of the entry's first product in the row's flat enumeration (u32: rows beyond 2^32 products are not mapped)
             u32 incl = len;
 #pragma unroll
             for (int d = 1; d < LA; d <<= 1) {
@@ -91,10 +113,8 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
             }
             if (p < end) aOff[p] = (u32)ops64 + incl - len;
             ops64 += (u64)__shfl_sync(gmask, incl, LA - 1, LA);   // every lane carries the running row total
-        } else {
-            ops64 += (u64)len;
+            if (aSeg && p < end) aSeg[p] = make_uint2(bs, be);
         }
-        if (aSeg && p < end) aSeg[p] = make_uint2(bs, be);
     }
 #pragma unroll
     for (int d = LA / 2; d >= 1; d >>= 1) {
@@ -111,6 +131,10 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
         rowMin[row] = cmin;
         rowMax[row] = cmax;
         const int bin = classify_row(ops, aLen, ops ? cmax - cmin + 1u : 0u, sortMax);
+        if (mapLen) {   // products of the row when its class records a rank map in the symbolic phase
+            const bool mapped = bin >= BIN_SORT0 + mapMinClass && (bin < BIN_SORT0 + NUM_WARP_SORT || (mapCta && bin < BIN_DENSE_LOCAL));
+            mapLen[row] = mapped ? ops : 0u;
+        }
         if (bin < 0)
             rowNnz[row] = 0;
         else {
@@ -140,21 +164,19 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff)
+                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff, u32 *mapLen, bool mapCta, int mapMinClass)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
     const int threads = 256;
-    if (avg <= 3.0) {
-        const u32 grid = (u32)(((u64)rows * 2 + threads - 1) / threads);
-        k_analyze<2><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff);
-    } else if (avg <= 24.0) {
-        const u32 grid = (u32)(((u64)rows * 8 + threads - 1) / threads);
-        k_analyze<8><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff);
-    } else {
-        const u32 grid = (u32)(((u64)rows * 32 + threads - 1) / threads);
-        k_analyze<32><<<grid, threads, 0, lc.stream>>>(rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff);
-    }
+#define SB_ANALYZE(LA)                                                                                                     \
+    k_analyze<LA><<<(u32)(((u64)rows * LA + threads - 1) / threads), threads, 0, lc.stream>>>(                             \
+        rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff, mapLen, mapCta, mapMinClass)
+    if (avg <= 3.0) SB_ANALYZE(2);
+    else if (avg <= 6.0) SB_ANALYZE(4);
+    else if (avg <= 24.0) SB_ANALYZE(8);
+    else SB_ANALYZE(32);
+#undef SB_ANALYZE
     ++*lc.launches;
 }
 
@@ -167,8 +189,8 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
                                                      const u32 *__restrict__ rowOps,
                                                      const u32 *__restrict__ rowMin,
                                                      const u32 *__restrict__ rowMax, u32 *__restrict__ perm,
-                                                     Scalars *sc, u32 sortMax, u32 *__restrict__ mapLen,
-                                                     bool mapCta, int mapMinClass)
+                                                     Scalars *sc, u32 sortMax, const u64 *__restrict__ mapBase,
+                                                     RowDesc *__restrict__ desc)
 {
     __shared__ u32 sCnt[NUM_BINS];
     __shared__ u32 sBase[NUM_BINS];
@@ -181,10 +203,6 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
         const u32 ops = rowOps[row];
         bin = classify_row(ops, aRp[row + 1] - aRp[row], ops ? rowMax[row] - rowMin[row] + 1u : 0u, sortMax);
         if (bin >= 0) rank = atomicAdd(&sCnt[bin], 1u);
-        if (mapLen) {
-            const bool mapped = bin >= BIN_SORT0 + mapMinClass && (bin < BIN_SORT0 + NUM_WARP_SORT || (mapCta && bin < BIN_DENSE_LOCAL));
-            mapLen[row] = mapped ? ops : 0u;
-        }
     }
     __syncthreads();
     if (threadIdx.x < NUM_BINS) {
@@ -194,40 +212,35 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u32 rows, const u32 *__rest
         sBase[threadIdx.x] = start + (c ? atomicAdd(&sc->binCursor[threadIdx.x], c) : 0u);
     }
     __syncthreads();
-    if (bin >= 0) perm[sBase[bin] + rank] = row;
+    if (bin >= 0) {
+        const u32 pos = sBase[bin] + rank;
+        perm[pos] = row;
+        if (desc) {   // row descriptor in bin order (common.cuh: RowDesc): every source is read coalesced by row here
+            RowDesc d;
+            d.aBeg = aRp[row];
+            d.aLen = aRp[row + 1] - d.aBeg;
+            d.n = rowOps[row];
+            d.row = row;
+            d.c0 = rowMin[row];
+            d.c1 = rowMax[row];
+            d.mapOff = mapBase[row];
+            desc[pos] = d;
+        }
+    }
 }
 
 void launch_bin_scatter(const LaunchCtx &lc, u32 rows, const u32 *aRp, const u32 *rowOps, const u32 *rowMin,
-                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, u32 *mapLen, bool mapCta, int mapMinClass)
+                        const u32 *rowMax, u32 *perm, Scalars *sc, u32 sortMax, const u64 *mapBase, RowDesc *desc)
 {
     if (rows == 0) return;
-    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, rowMin, rowMax, perm, sc, sortMax, mapLen,
-                                                             mapCta, mapMinClass);
+    k_bin_scatter<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, rowMin, rowMax, perm, sc, sortMax, mapBase, desc);
     ++*lc.launches;
 }
 
 // ------------------------------------------------------------------------------------------
-// Row descriptors of the mapped classes (common.cuh: RowDesc), in perm order.
+// Row descriptors of the mapped classes (common.cuh: RowDesc), in perm order: written by k_bin_scatter, switched to
+// the numeric flavour (position / length in C) here once row_offsets are scanned.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_build_desc(const u32 *__restrict__ perm, u32 count,
-                                                    const u32 *__restrict__ aRp, const u32 *__restrict__ rowOps,
-                                                    const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax,
-                                                    const u64 *__restrict__ mapBase, RowDesc *__restrict__ desc)
-{
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const u32 row = perm[j];
-    RowDesc d;
-    d.aBeg = aRp[row];
-    d.aLen = aRp[row + 1] - d.aBeg;
-    d.n = rowOps[row];
-    d.row = row;
-    d.c0 = rowMin[row];
-    d.c1 = rowMax[row];
-    d.mapOff = mapBase[row];
-    desc[j] = d;
-}
-
 __global__ void __launch_bounds__(256) k_desc_numeric(u32 count, const u32 *__restrict__ cRp, RowDesc *desc)
 {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,14 +249,6 @@ __global__ void __launch_bounds__(256) k_desc_numeric(u32 count, const u32 *__re
     const u32 b = cRp[row];
     desc[j].c0 = b;
     desc[j].c1 = cRp[row + 1] - b;
-}
-
-void launch_build_desc(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *rowOps,
-                       const u32 *rowMin, const u32 *rowMax, const u64 *mapBase, RowDesc *desc)
-{
-    if (count == 0) return;
-    k_build_desc<<<(count + 255) / 256, 256, 0, lc.stream>>>(perm, count, aRp, rowOps, rowMin, rowMax, mapBase, desc);
-    ++*lc.launches;
 }
 
 void launch_desc_numeric(const LaunchCtx &lc, u32 count, const u32 *cRp, RowDesc *desc)
@@ -415,6 +420,22 @@ __global__ void k_find_cuts(const u64 *__restrict__ prefix, u32 rows, u32 parts,
     const u32 c = cut_of(g);
     cuts[g] = c;
     if (g < parts && partProducts) partProducts[g] = prefix[cut_of(g + 1)] - prefix[c];
+}
+
+// cost of a row for the partition = products + wEntry * entries of the A row + wRow (saturating u32)
+__global__ void __launch_bounds__(256) k_row_cost(u32 rows, const u32 *__restrict__ aRp, u32 *__restrict__ rowOps, u32 wRow, u32 wEntry)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const u64 c = (u64)rowOps[r] + (u64)wEntry * (aRp[r + 1] - aRp[r]) + wRow;
+    rowOps[r] = c > 0xffffffffull ? 0xffffffffu : (u32)c;
+}
+
+void launch_row_cost(const LaunchCtx &lc, u32 rows, const u32 *aRp, u32 *rowOps, u32 wRow, u32 wEntry)
+{
+    if (rows == 0 || (wRow == 0 && wEntry == 0)) return;
+    k_row_cost<<<(rows + 255) / 256, 256, 0, lc.stream>>>(rows, aRp, rowOps, wRow, wEntry);
+    ++*lc.launches;
 }
 
 void launch_find_cuts(const LaunchCtx &lc, const u64 *prefix, u32 rows, u32 parts, u32 *cuts, u64 *partProducts)

@@ -608,3 +608,33 @@ def _seq_sum(x):
     for t in x[1:]:
         s = s + t        # same type, left to right: the order the kernel uses
     return s
+
+
+def test_deterministic_mode_is_bit_equal_to_the_oracle(ctx):
+    """Option "deterministic" (the reference is "not bit stable", config.ini:8-9): every entry of C is the sum of
+    its products in ascending k, products rounded before they are added -- the CPU oracle's order -- so values
+    are bit-identical to the oracle and from run to run, on every row class (lane-group and CTA sort classes,
+    sequential-k bitmap rows, recomputed bitmap rows, direct rows)."""
+    cases = [("rmat15", M.rmat(15, 16, seed=15), None),                 # rows up to > 16384 products: recomputed bitmap rows
+             ("fem", M.fem3d_like(9, 8, 7), None),                      # high compression: sequential-k kernel
+             ("wide band", M.banded_fem_like(n=6000, per_row=96, clusters=12, band=1500, seed=7), None),   # > 2048 entries per row
+             ("uniform", M.uniform_random(2000, 2000, 16, seed=4), None),
+             ("rect", M.uniform_random(700, 300, 5, seed=11), M.uniform_random(300, 1500, 7, seed=12))]
+    ctx.set_option("deterministic", 1)
+    try:
+        for name, A, B in cases:
+            want = oracle_multiply(A, A if B is None else B)
+            got, st = gpu_multiply(ctx, A, B)
+            np.testing.assert_array_equal(got.row_offsets, want.row_offsets, err_msg=name)
+            np.testing.assert_array_equal(got.col_ids, want.col_ids, err_msg=name)
+            np.testing.assert_array_equal(got.data, want.data, err_msg=f"{name}: values must be bit-equal to the oracle")
+            again, _ = gpu_multiply(ctx, A, B)
+            np.testing.assert_array_equal(again.data, got.data, err_msg=f"{name}: run-to-run")
+        A32 = M.rmat(13, 16, seed=13, dtype=np.float32)
+        a, _ = gpu_multiply(ctx, A32)
+        b, _ = gpu_multiply(ctx, A32)
+        np.testing.assert_array_equal(a.data, b.data)
+    finally:
+        ctx.set_option("deterministic", 0)
+    # and the default mode still agrees to 1e-6
+    check_case(ctx, cases[0][1], what="default after deterministic")

@@ -85,3 +85,26 @@ def test_runspeck_rectangular_uses_transpose(tmp_path):
 def test_runspeck_missing_file_message(tmp_path):
     out = run([str(tmp_path / "nope.mtx")], tmp_path)
     assert out.returncode != 0 and "could not load mtx file" in out.stdout
+
+
+def test_runspeck_devices_key_runs_the_sharded_path(tmp_path):
+    """`Devices=` (new ini key): A is cut into product-balanced slabs, one per listed device, the slabs of C are
+    concatenated on the first device and checked against cuSPARSE.  On a one-GPU box the list repeats device 0
+    (contexts may share a device); on a multi-GPU box it names distinct devices."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = ",".join(str(g if ndev >= 3 else 0) for g in range(3))
+    A = M.rmat(11, 16, seed=5)
+    mtx = tmp_path / "rmat11.mtx"
+    write_mtx(mtx, A)
+    ini = tmp_path / "config.ini"
+    ini.write_text(f"CompareResult=true\nIterationsWarmUp=1\nIterationsExecution=2\nDevices={devices}\n")
+    out = run([str(mtx), str(ini)], tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Error: Matrix incorrect" not in out.stdout and "ERROR" not in out.stdout, out.stdout
+    import oracle
+    rp, _, _ = oracle.spgemm(A.row_offsets, A.col_ids, A.data, A.row_offsets, A.col_ids, A.data, A.cols)
+    assert f" var-SpGEMM -> NNZ: {int(rp[-1])}" in out.stdout
+    assert re.search(r" var-SpGEMM SpGEMM: [0-9.e+-]+ ms", out.stdout)
+    assert len(re.findall(r"device \d+: rows \[\d+, \d+\)", out.stdout)) == 3
+    assert "3 devices" in out.stdout and "var-SpGEMM concat:" in out.stdout
