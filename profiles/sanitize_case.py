@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Small multiplies that touch every kernel family, for compute-sanitizer (memcheck / racecheck / initcheck):
+the smoke matrix, the class-boundary rows of tests/test_gpu_parity.py, a FEM-like matrix (bitmap rows, sequential-k
+kernel in both staging variants), the deterministic mode.  Checks every result against the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle  # noqa: E402
+from speck_b200 import api, matrices as M  # noqa: E402
+from test_gpu_parity import _rows_with_products  # noqa: E402
+
+
+def check(ctx, A, B=None, what=""):
+    dA = ctx.upload(A)
+    dB = dA if B is None else ctx.upload(B)
+    C = ctx.download(ctx.multiply(dA, dB))
+    Bh = A if B is None else B
+    rp, ci, v = oracle.spgemm(A.row_offsets, A.col_ids, A.data, Bh.row_offsets, Bh.col_ids, Bh.data, Bh.cols)
+    assert np.array_equal(C.row_offsets, rp) and np.array_equal(C.col_ids, ci), what
+    assert np.allclose(C.data, v, rtol=1e-6, atol=0), what
+    print("ok", what, "P =", ctx.stats()["products"], flush=True)
+
+
+with api.Context(0) as ctx:
+    check(ctx, M.rmat(12, 16, seed=7), what="smoke matrix")
+    targets = []
+    for c in range(0, 12):
+        b = 4 << c
+        targets += [b - 1, b, b + 1]
+    targets += [1, 2, 3, 8255, 8256, 12345, 16383, 16384, 16385, 20000]
+    A, B = _rows_with_products(targets, cols=1 << 18, nb=256)
+    check(ctx, A, B, what="class boundaries (mapped)")
+    ctx.set_option("rank_map", 0)
+    check(ctx, A, B, what="class boundaries (self-contained numeric kernels)")
+    ctx.set_option("rank_map", 1)
+    ctx.set_option("flat_sym", 0)
+    check(ctx, A, B, what="class boundaries (register-slot symbolic kernel)")
+    ctx.set_option("flat_sym", 1)
+    F = M.fem3d_like(7, 6, 5)
+    for v in (1, 2, 0):
+        ctx.set_option("dense_seq", v)
+        check(ctx, F, what=f"FEM-like, dense_seq={v}")
+    ctx.set_option("dense_seq", 1)
+    ctx.set_option("deterministic", 1)
+    check(ctx, M.rmat(13, 16, seed=13), what="deterministic mode")
+    ctx.set_option("deterministic", 0)
+print("all ok")

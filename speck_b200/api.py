@@ -18,7 +18,7 @@ import numpy as np
 from .matrices import HostCSR
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libspeck_b200.so")
+LIB_PATH = os.environ.get("SPECK_B200_LIB") or os.path.join(_HERE, "_lib", "libspeck_b200.so")   # override: kernel experiments
 
 NUM_CLASSES = 32
 BIN_NAMES = (["direct"] + [f"sort{4 << c}" for c in range(8)] + [f"sort{512 * w}" for w in range(2, 17)]

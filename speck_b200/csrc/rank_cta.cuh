@@ -426,6 +426,9 @@ struct MapCtaLayout {
     static constexpr size_t SMEM = STAB + al(CAP / 32 * 2);
 };
 
+#ifndef SB_MAP_GU
+#define SB_MAP_GU 4
+#endif
 #ifndef SB_MAP_CTA_THREADS_PER_SM
 #define SB_MAP_CTA_THREADS_PER_SM 1536
 #endif
@@ -482,7 +485,7 @@ k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
             for (u32 b = (excl + 31) >> 5; b <= bLast; ++b) sTab[b] = (unsigned short)tid;
         }
         __syncthreads();
-        constexpr int GU = E < 4 ? E : 4;   // products per thread in flight
+        constexpr int GU = E < SB_MAP_GU ? E : SB_MAP_GU;   // products per thread in flight
         const u32 first = max(myFirst, base), last = min(min(myFirst + EP, n), base + total);
         const u32 mine = first < last ? last - first : 0u;   // this thread's products in the batch
         SegWalk<T, true> walk;

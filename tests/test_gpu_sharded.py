@@ -103,3 +103,28 @@ def test_shard_plan_empty_slabs_and_rectangular():
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_partition_rows_with_row_and_entry_costs(ctx):
+    """partition_row_cost / partition_entry_cost: the cuts balance products + 2 * nnz(A row) + 8 per row (what
+    bench.py --gpus N uses: tiny rows cost more than their products say)."""
+    A = M.rmat(13, 4, seed=9)
+    dA = ctx.upload(A)
+    ctx.set_option("partition_row_cost", 8)
+    ctx.set_option("partition_entry_cost", 2)
+    try:
+        cuts, cost = ctx.partition_rows(dA, dA, 4)
+    finally:
+        ctx.set_option("partition_row_cost", 0)
+        ctx.set_option("partition_entry_cost", 0)
+        dA.free()
+    blen = np.diff(A.row_offsets.astype(np.int64))
+    alen = np.diff(A.row_offsets.astype(np.int64))
+    ops = np.zeros(A.rows, np.int64)
+    nz = alen > 0
+    ops[nz] = np.add.reduceat(blen[A.col_ids], A.row_offsets[:-1].astype(np.int64)[nz])
+    c = ops + 2 * alen + 8
+    prefix = np.concatenate([[0], np.cumsum(c)])
+    want = np.concatenate([[0], np.searchsorted(prefix, (np.arange(1, 4) * prefix[-1]) // 4, side="left"), [A.rows]])
+    np.testing.assert_array_equal(cuts.astype(np.int64), want)
+    assert [int(x) for x in cost] == [int(prefix[want[g + 1]] - prefix[want[g]]) for g in range(4)]
