@@ -1,7 +1,8 @@
 // include/Config.h -- key/value run configuration read from an INI file (reference
 // include/Config.h + source/Config.cpp over inih).  Only the six keys the reference driver ever
 // reads are kept, plus `Device` for selecting the GPU and `Devices` (comma-separated list,
-// e.g. Devices=0,1,2,3) for the row-sharded multi-GPU run.
+// e.g. Devices=0,1,2,3) for the row-sharded multi-GPU run and `GpuConvert` (COO -> CSR of a freshly
+// parsed .mtx on the device instead of the host sort).
 #pragma once
 #include <map>
 #include <string>
@@ -9,7 +10,7 @@
 class Config {
 public:
     enum Key { InputFile, IterationsWarmUp, IterationsExecution, TrackIndividualTimes, TrackCompleteTimes,
-               CompareResult, Device, Devices };
+               CompareResult, Device, Devices, GpuConvert };
 
     static void init(std::string path);   // parse `path` (section-less key=value, ';'/'#' comments)
     static void init();                   // no file: every get* returns its fallback

@@ -221,6 +221,8 @@ int speck_b200_sharded_destroy(speck_shard_plan *plan);
  *   "deterministic"     1: values bit-reproducible and in the CPU oracle's summation order (ascending k, products
  *                       rounded before they are added); slower: no rank map, sort classes, rows that accumulate
  *                       with atomics are recomputed.  Default 0 (like the reference: "not bit stable")
+ *   "tiered_analysis"   1: the analysis gathers B's row_offsets only and fetches column extents in a second pass for
+ *                       rows with >= 128 products; 0 (default): one 16-byte row summary per A entry (measured faster)
  *   "spin_wait"         1 (default): the two mid-pipeline scalar read-backs poll mapped pinned memory, 0: they use
  *                       cudaMemcpyAsync + cudaStreamSynchronize
  *   "partition_row_cost", "partition_entry_cost"   speck_b200_partition_rows balances products + entry_cost * nnz(A row)

@@ -84,6 +84,9 @@ struct speck_ctx {
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
     u32 partRowCost = 0, partEntryCost = 0;   // partition_rows: cost of a row = products + partEntryCost * entries + partRowCost
+    int tieredAnalysis = 0;   // 1: two-pass analysis (row_offsets pairs first, column extents only for rows that use them);
+                              // measured slower even when B's 16-byte row summaries miss the L2 (R-MAT scale 24: analysis
+                              // 1.70 -> 1.97 ms), so it is off; kept as a tested option
     bool deterministic = false;   // bit-reproducible values in the oracle's summation order (slower): sort classes
                               // up to 8192 products, sequential-k kernel for every local bitmap row that fits, the
                               // remaining bitmap rows recomputed by k_det_rows
@@ -229,7 +232,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (c->segNum && (rc = ensure(c->aOff, (size_t)A->nnz * sizeof(u32)))) return rc;
         if ((rc = ensure(c->desc, (size_t)rows * sizeof(RowDesc)))) return rc;
     }
-    if ((rc = ensure(c->rowInfo, (size_t)B->rows * sizeof(uint4)))) return rc;
+    if (c->tieredAnalysis != 1 && (rc = ensure(c->rowInfo, (size_t)B->rows * sizeof(uint4)))) return rc;
     u32 *cRp = C->row_offsets;
     if (!(C->rows == A->rows && cRp != nullptr)) {
         if (cRp) cudaFree(cRp);
@@ -243,11 +246,14 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     CU_TRY(cudaMemsetAsync(c->dSc, 0, sizeof(Scalars), c->main));
 
     // ---- analysis + binning
-    launch_row_info(lc, (u32)B->rows, bRp, bCi, (uint4 *)c->rowInfo.p);
+    // B-row summaries: 16 B per row of B, one gather per A entry (option tiered_analysis = 1: row_offsets pairs only,
+    // column extents in a second pass for the rows that use them)
+    const bool tiered = c->tieredAnalysis == 1;
+    if (!tiered) launch_row_info(lc, (u32)B->rows, bRp, bCi, (uint4 *)c->rowInfo.p);
     launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
-                   wantMap ? (uint2 *)c->aSeg.p : nullptr, (const uint4 *)c->rowInfo.p,
+                   wantMap ? (uint2 *)c->aSeg.p : nullptr, tiered ? nullptr : (const uint4 *)c->rowInfo.p,
                    wantMap && c->segNum ? (u32 *)c->aOff.p : nullptr, wantMap ? (u32 *)c->mapLen.p : nullptr, useRank,
-                   c->mapMinClass);
+                   c->mapMinClass, tiered ? min(128u, sortMax + 1u) : 0u);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
     launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (const u64 *)c->mapBase.p : nullptr,
                        wantMap ? (RowDesc *)c->desc.p : nullptr);
@@ -1156,6 +1162,11 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "partition_row_cost") || !strcmp(key, "partition_entry_cost")) {
         if (value < 0 || value > 1024) return fail(SPECK_ERR_INVALID, "%s must be in [0, 1024]", key);
         (key[10] == 'r' ? c->partRowCost : c->partEntryCost) = (u32)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "tiered_analysis")) {
+        if (value < -1 || value > 1) return fail(SPECK_ERR_INVALID, "tiered_analysis must be -1, 0 or 1");
+        c->tieredAnalysis = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "deterministic")) {

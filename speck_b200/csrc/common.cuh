@@ -103,7 +103,8 @@ struct LaunchCtx {
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
                     uint2 *aSeg, const uint4 *rowInfo, u32 *aOff = nullptr, u32 *mapLen = nullptr, bool mapCta = false,
-                    int mapMinClass = 0);
+                    int mapMinClass = 0, u32 extentMinOps = 0 /* > 0 and no rowInfo: column extents only for rows with at
+                    least this many products (two-pass analysis for matrices whose B summaries would miss the L2) */);
 // rowInfo[k] = (begin, end, first column, last column) of B row k: one gather per A entry in the analysis
 void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *bCi, uint4 *rowInfo);
 // descriptors (written by launch_bin_scatter, symbolic flavour: c0/c1 = column extent) switched to the numeric

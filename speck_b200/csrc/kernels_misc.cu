@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                                                  u32 *__restrict__ rowMax, u32 *__restrict__ rowNnz, Scalars *sc,
                                                  u32 sortMax, uint2 *__restrict__ aSeg,
                                                  const uint4 *__restrict__ rowInfo, u32 *__restrict__ aOff,
-                                                 u32 *__restrict__ mapLen, bool mapCta, int mapMinClass)
+                                                 u32 *__restrict__ mapLen, bool mapCta, int mapMinClass,
+                                                 u32 extentMinOps)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -63,10 +64,15 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
     const u32 beg = row < rows ? aRp[row] : 0u, end = row < rows ? aRp[row + 1] : 0u;
     aLen = end - beg;
     // B-row summary of one A entry: (begin, end, first column, last column); empty rows carry (0xffffffff, 0)
+    // extentMinOps > 0 (no rowInfo table: B has so many rows that the 16-byte summaries would miss the L2): the first
+    // pass gathers only the row_offsets pair (4 B per row of B, L2-resident); the first / last columns are gathered in a
+    // second pass for the rows with at least extentMinOps products -- the only ones whose extent is ever used
+    // (banded test of classify_row, rank and bitmap kernels); the others keep the placeholder extent [0, 0].
+    const bool tiered = !rowInfo && extentMinOps > 0;
     auto fetch = [&](u32 k) -> uint4 {
         if (rowInfo) return __ldg(rowInfo + k);
         uint4 ri = make_uint4(__ldg(bRp + k), __ldg(bRp + k + 1), 0xffffffffu, 0u);
-        if (ri.y > ri.x) {
+        if (!tiered && ri.y > ri.x) {
             ri.z = __ldg(bCi + ri.x);
             ri.w = __ldg(bCi + ri.y - 1);
         }
@@ -116,9 +122,37 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
             if (aSeg && p < end) aSeg[p] = make_uint2(bs, be);
         }
     }
+    if (!aOff) {
+#pragma unroll
+        for (int d = LA / 2; d >= 1; d >>= 1) ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
+    }
+    if (tiered) {
+        cmin = 0xffffffffu; cmax = 0u;
+        if (ops64 >= (u64)extentMinOps) {   // uniform in the lane group: every lane holds the row total
+            for (u32 p0 = beg + lane; p0 < end; p0 += 2 * LA) {
+                u32 bs[2], be[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    bs[u] = be[u] = 0;
+                    if (p0 + u * LA < end) {
+                        const u32 k = __ldg(aCi + p0 + u * LA);
+                        bs[u] = __ldg(bRp + k);
+                        be[u] = __ldg(bRp + k + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (be[u] > bs[u]) {
+                        cmin = min(cmin, __ldg(bCi + bs[u]));
+                        cmax = max(cmax, __ldg(bCi + be[u] - 1));
+                    }
+            }
+        } else {
+            cmin = 0u;
+        }
+    }
 #pragma unroll
     for (int d = LA / 2; d >= 1; d >>= 1) {
-        if (!aOff) ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
         cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, d));
         cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
     }
@@ -164,14 +198,16 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
-                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff, u32 *mapLen, bool mapCta, int mapMinClass)
+                    uint2 *aSeg, const uint4 *rowInfo, u32 *aOff, u32 *mapLen, bool mapCta, int mapMinClass,
+                    u32 extentMinOps)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
     const int threads = 256;
 #define SB_ANALYZE(LA)                                                                                                     \
     k_analyze<LA><<<(u32)(((u64)rows * LA + threads - 1) / threads), threads, 0, lc.stream>>>(                             \
-        rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff, mapLen, mapCta, mapMinClass)
+        rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff, mapLen, mapCta, mapMinClass,  \
+        extentMinOps)
     if (avg <= 3.0) SB_ANALYZE(2);
     else if (avg <= 6.0) SB_ANALYZE(4);
     else if (avg <= 24.0) SB_ANALYZE(8);

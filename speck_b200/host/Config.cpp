@@ -40,6 +40,7 @@ const char *Config::name(Key key)
         case CompareResult: return "compareresult";
         case Device: return "device";
         case Devices: return "devices";
+        case GpuConvert: return "gpuconvert";
     }
     return "";
 }

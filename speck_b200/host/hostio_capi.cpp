@@ -31,7 +31,7 @@ bool key_of(const char *name, Config::Key &k)
         {"inputfile", Config::InputFile}, {"iterationswarmup", Config::IterationsWarmUp},
         {"iterationsexecution", Config::IterationsExecution}, {"trackindividualtimes", Config::TrackIndividualTimes},
         {"trackcompletetimes", Config::TrackCompleteTimes}, {"compareresult", Config::CompareResult},
-        {"device", Config::Device}, {"devices", Config::Devices}};
+        {"device", Config::Device}, {"devices", Config::Devices}, {"gpuconvert", Config::GpuConvert}};
     for (auto &e : table)
         if (s == e.n) { k = e.k; return true; }
     return false;

@@ -638,3 +638,22 @@ def test_deterministic_mode_is_bit_equal_to_the_oracle(ctx):
         ctx.set_option("deterministic", 0)
     # and the default mode still agrees to 1e-6
     check_case(ctx, cases[0][1], what="default after deterministic")
+
+
+@pytest.mark.parametrize("sort_max_value", [16384, 1024, 64])
+def test_tiered_analysis(ctx, sort_max_value):
+    """tiered_analysis=1: the analysis gathers only B's row_offsets and fetches column extents in a second pass for
+    the rows that use them; same results on every row class."""
+    ctx.set_option("tiered_analysis", 1)
+    ctx.set_option("sort_max", sort_max_value)
+    try:
+        check_case(ctx, M.rmat(14, 16, seed=14), what="tiered rmat14")
+        check_case(ctx, M.banded_fem_like(n=4000, per_row=64, clusters=8, band=300, seed=41), what="tiered banded")
+        check_case(ctx, M.fem3d_like(9, 8, 7), what="tiered fem")
+        check_case(ctx, M.webbase_like(n=50000, seed=3), what="tiered web-like")
+        A = M.uniform_random(700, 300, 5, seed=11)
+        B = M.uniform_random(300, 1 << 22, 7, seed=12)     # wide: three-level rank kernels / 64-bit keys
+        check_case(ctx, A, B, what="tiered wide")
+    finally:
+        ctx.set_option("tiered_analysis", 0)
+        ctx.set_option("sort_max", 16384)

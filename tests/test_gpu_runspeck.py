@@ -108,3 +108,22 @@ def test_runspeck_devices_key_runs_the_sharded_path(tmp_path):
     assert re.search(r" var-SpGEMM SpGEMM: [0-9.e+-]+ ms", out.stdout)
     assert len(re.findall(r"device \d+: rows \[\d+, \d+\)", out.stdout)) == 3
     assert "3 devices" in out.stdout and "var-SpGEMM concat:" in out.stdout
+
+
+def test_runspeck_gpu_convert_writes_the_same_cache(tmp_path):
+    """GpuConvert=true: COO -> CSR of the parsed .mtx on the device; the .hicsr cache must be byte-identical to the
+    one the host conversion writes (same order, duplicates kept)."""
+    A = M.rmat(10, 8, seed=3)
+    outs = {}
+    for mode in ("false", "true"):
+        d = tmp_path / mode
+        d.mkdir()
+        mtx = d / "m.mtx"
+        write_mtx(mtx, A)
+        ini = d / "config.ini"
+        ini.write_text(f"CompareResult=true\nIterationsWarmUp=1\nIterationsExecution=1\nGpuConvert={mode}\n")
+        out = run([str(mtx), str(ini)], d)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "Error: Matrix incorrect" not in out.stdout
+        outs[mode] = open(str(mtx) + "d_.hicsr", "rb").read()
+    assert outs["true"] == outs["false"]
