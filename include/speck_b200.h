@@ -228,6 +228,8 @@ int speck_b200_sharded_destroy(speck_shard_plan *plan);
  *   "partition_row_cost", "partition_entry_cost"   speck_b200_partition_rows balances products + entry_cost * nnz(A row)
  *                       + row_cost per row instead of products alone (default 0, 0).  Measured on the config-5
  *                       matrix: a row costs about as much as 7 products, an entry of A about 1.5 (profiles/r2_notes.md)
+ *   "col_direct"        1..3: large mapped numeric shapes stage values only and write column ids straight to C
+ *                       (measured slower; default 0)
  *   "seg_num", "hash_count"        experiments kept for the record (profiles/r2_notes.md), off by default
  *   "release_workspace" 1 frees the pooled workspace now. */
 int speck_b200_set_option(speck_ctx *ctx, const char *key, long long value);

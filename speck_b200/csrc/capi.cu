@@ -92,6 +92,8 @@ struct speck_ctx {
                               // remaining bitmap rows recomputed by k_det_rows
     int denseSeq = 1;         // banded / high-compression rows: sequential-k numeric kernel (dense_seq.cuh): 0 = off,
                               // 1 = B segments loaded by the lanes, 2 = staged by TMA bulk copies
+    int colDirect = 0;        // mapped numeric CTA kernels: 1..3 = the large shapes stage values only and write column ids
+                              // straight to C (rank_cta.cuh: COLDIRECT); measured slower (profiles/r2_notes.md), off
     int segNum = 0;           // mapped numeric CTA classes: 1 = segment-major kernel (map_seg.cuh; measured slower: fewer
                               // loads in flight per SM, profiles/r2_notes.md), 0 = k_map_rows_cta
     int flatSym = 1;          // mapped two-level symbolic rank kernel: 1 = flat staged variant (rank_flat.cuh), 0 = rank_cta.cuh
@@ -415,7 +417,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             if (rankMap && c->segNum)
                 launch_map_seg<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, (const u32 *)c->aOff.p, aV, bCi, bV, rankMap, cCi, cV);
             else if (rankMap)
-                launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
+                launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV, c->colDirect);
             else if (rankLevels == 2)
                 launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
                                        rowMax, cRp, cCi, cV);
@@ -1176,6 +1178,11 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "dense_seq")) {
         if (value < 0 || value > 2) return fail(SPECK_ERR_INVALID, "dense_seq must be 0, 1 or 2");
         c->denseSeq = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "col_direct")) {
+        if (value < 0 || value > 3) return fail(SPECK_ERR_INVALID, "col_direct must be in [0, 3]");
+        c->colDirect = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "spin_wait")) {

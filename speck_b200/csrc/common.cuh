@@ -150,7 +150,8 @@ void launch_map_numeric(const LaunchCtx &lc, int sortClass, const RowDesc *desc,
 template <typename T>
 void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
                             const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi,
-                            T *cV);
+                            T *cV, int colDirect = 0 /* 1: the 1024-thread shapes write column ids straight to C and
+                            stage only the values (two CTAs per SM), 2: the 512-thread shape as well */);
 template <typename T>
 void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
                          const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi,

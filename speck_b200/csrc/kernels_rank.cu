@@ -74,14 +74,20 @@ void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, 
 template <typename T>
 void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
                             const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi,
-                            T *cV)
+                            T *cV, int colDirect)
 {
     if (count == 0) return;
 #define SB_MAP_NUM(TH, E) launch_map_rows_cta<TH, E, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
+#define SB_MAP_NUM_CD(TH, E) launch_map_rows_cta<TH, E, T, true>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
     if (capProducts <= 32 * RANK_E) SB_MAP_NUM(32, RANK_E);
     else if (capProducts <= 64 * RANK_E) SB_MAP_NUM(64, RANK_E);
+    else if (colDirect && capProducts > 1024 * RANK_E) SB_MAP_NUM_CD(1024, 2 * RANK_E);   // 8193..16384 products
+    else if (colDirect == 3 && capProducts > 512 * RANK_E) SB_MAP_NUM_CD(512, 2 * RANK_E);   // 4097..8192 as 512 x 16
+    else if (colDirect && capProducts > 512 * RANK_E) SB_MAP_NUM_CD(1024, RANK_E);       // 4097..8192: two CTAs per SM
+    else if (colDirect > 1 && capProducts > 256 * RANK_E) SB_MAP_NUM_CD(512, RANK_E);
     else SB_RANK_SHAPES(SB_MAP_NUM);
 #undef SB_MAP_NUM
+#undef SB_MAP_NUM_CD
 }
 
 #define SB_INST(T)                                                                                                     \
@@ -89,7 +95,7 @@ void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc 
                                          const u32 *, const u32 *, const T *, const u32 *, const u32 *, const u32 *,   \
                                          const u32 *, u32 *, T *);                                                     \
     template void launch_map_numeric_cta<T>(const LaunchCtx &, u32, const RowDesc *, u32, const uint2 *, const T *,    \
-                                            const u32 *, const T *, const unsigned short *, u32 *, T *);
+                                            const u32 *, const T *, const unsigned short *, u32 *, T *, int);
 SB_INST(double)
 SB_INST(float)
 #undef SB_INST

@@ -413,14 +413,17 @@ void launch_rank_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32
 // Numeric phase of a mapped row (CTA per row): gather, multiply, scatter by the recorded rank into a
 // shared staging row, write the row to C coalesced.  No bitmaps, no scans beyond the B-row lengths.
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int E, typename T>
+// COLDIRECT: the column ids of the first products go straight to C (scattered 4-byte stores inside the row's range,
+// merged by the L2 before they reach DRAM) and only the values are staged: two thirds of the shared memory, which
+// lets the 1024-thread shapes keep two CTAs per SM instead of one.
+template <int THREADS, int E, typename T, bool COLDIRECT = false>
 struct MapCtaLayout {
     static constexpr size_t al(size_t b) { return (b + 15) / 16 * 16; }
     static constexpr size_t CAP = (size_t)THREADS * E;
     static constexpr size_t OUTVAL = 0;
     static constexpr size_t SAV = OUTVAL + al(CAP * sizeof(T));
     static constexpr size_t OUTCOL = SAV + al(THREADS * sizeof(T));
-    static constexpr size_t SINCL = OUTCOL + al(CAP * 4);
+    static constexpr size_t SINCL = OUTCOL + (COLDIRECT ? 0 : al(CAP * 4));
     static constexpr size_t SBS = SINCL + al(THREADS * 4);
     static constexpr size_t STAB = SBS + al(THREADS * 4);
     static constexpr size_t SMEM = STAB + al(CAP / 32 * 2);
@@ -432,13 +435,13 @@ struct MapCtaLayout {
 #ifndef SB_MAP_CTA_THREADS_PER_SM
 #define SB_MAP_CTA_THREADS_PER_SM 1536
 #endif
-template <int THREADS, int E, typename T>
-__global__ void __launch_bounds__(THREADS, SB_MAP_CTA_THREADS_PER_SM / THREADS)
+template <int THREADS, int E, typename T, bool COLDIRECT>
+__global__ void __launch_bounds__(THREADS, (COLDIRECT && THREADS == 1024 && E == 8) ? 2 : ((SB_MAP_CTA_THREADS_PER_SM / THREADS) > 0 ? (SB_MAP_CTA_THREADS_PER_SM / THREADS) : 1))
 k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg, const T *__restrict__ aV,
                const u32 *__restrict__ bCi, const T *__restrict__ bV, const unsigned short *__restrict__ rankMap,
                u32 *__restrict__ cCi, T *__restrict__ cV)
 {
-    using L = MapCtaLayout<THREADS, E, T>;
+    using L = MapCtaLayout<THREADS, E, T, COLDIRECT>;
     constexpr u32 NONE = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     T *outVal = reinterpret_cast<T *>(smemRaw + L::OUTVAL);
@@ -518,13 +521,15 @@ k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
                     const u32 r = code[u] & MAP_RANK_MASK;
                     const T pr = av[u] * bv[u];
                     if (multi) {
-                        if (!(code[u] & MAP_DUP)) outCol[r] = cc[u];
+                        if (!(code[u] & MAP_DUP)) {
+                            if (COLDIRECT) cCi[cBase + r] = cc[u]; else outCol[r] = cc[u];
+                        }
                         atomicAdd(&outVal[r], pr);
                     } else if (code[u] & MAP_DUP) {
                         dup |= 1u << (i0 + u);
                     } else {
                         outVal[r] = pr;
-                        outCol[r] = cc[u];
+                        if (COLDIRECT) cCi[cBase + r] = cc[u]; else outCol[r] = cc[u];
                     }
                 }
             }
@@ -544,17 +549,17 @@ k_map_rows_cta(const RowDesc *__restrict__ desc, const uint2 *__restrict__ aSeg,
     }
 #pragma unroll 1
     for (u32 j = tid; j < nnzRow; j += THREADS) {
-        cCi[cBase + j] = outCol[j];
+        if (!COLDIRECT) cCi[cBase + j] = outCol[j];
         cV[cBase + j] = outVal[j];
     }
 }
 
-template <int THREADS, int E, typename T>
+template <int THREADS, int E, typename T, bool COLDIRECT = false>
 void launch_map_rows_cta(const LaunchCtx &lc, const RowDesc *desc, u32 count, const uint2 *aSeg, const T *aV,
                          const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi, T *cV)
 {
-    using L = MapCtaLayout<THREADS, E, T>;
-    auto kern = k_map_rows_cta<THREADS, E, T>;
+    using L = MapCtaLayout<THREADS, E, T, COLDIRECT>;
+    auto kern = k_map_rows_cta<THREADS, E, T, COLDIRECT>;
     if (L::SMEM > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
     kern<<<count, THREADS, L::SMEM, lc.stream>>>(desc, aSeg, aV, bCi, bV, rankMap, cCi, cV);

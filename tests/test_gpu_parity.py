@@ -641,6 +641,18 @@ def test_deterministic_mode_is_bit_equal_to_the_oracle(ctx):
 
 
 @pytest.mark.parametrize("sort_max_value", [16384, 1024, 64])
+def test_col_direct_variants(ctx):
+    """col_direct = 1..3: the large mapped numeric shapes write column ids straight to C (kept as a tested option)."""
+    A = M.rmat(15, 16, seed=15)
+    try:
+        for v in (1, 2, 3):
+            ctx.set_option("col_direct", v)
+            check_case(ctx, A, what=f"col_direct={v}")
+    finally:
+        ctx.set_option("col_direct", 0)
+
+
+@pytest.mark.parametrize("sort_max_value", [16384, 1024, 64])
 def test_tiered_analysis(ctx, sort_max_value):
     """tiered_analysis=1: the analysis gathers only B's row_offsets and fetches column extents in a second pass for
     the rows that use them; same results on every row class."""
