@@ -38,7 +38,10 @@ struct FlatLayout {
 
 // lanes per B segment while staging: short B rows dominate by count, eight lanes (one 32-byte sector) keep most
 // lanes busy on them
-constexpr int FLAT_SG = 8;
+#ifndef SB_FLAT_SG
+#define SB_FLAT_SG 8
+#endif
+constexpr int FLAT_SG = SB_FLAT_SG;
 
 template <int THREADS, int E>
 __global__ void __launch_bounds__(THREADS)

@@ -640,7 +640,6 @@ def test_deterministic_mode_is_bit_equal_to_the_oracle(ctx):
     check_case(ctx, cases[0][1], what="default after deterministic")
 
 
-@pytest.mark.parametrize("sort_max_value", [16384, 1024, 64])
 def test_col_direct_variants(ctx):
     """col_direct = 1..3: the large mapped numeric shapes write column ids straight to C (kept as a tested option)."""
     A = M.rmat(15, 16, seed=15)
