@@ -84,10 +84,13 @@ struct speck_ctx {
     int mapMinClass = 0;      // lane-group classes below this one (rows of <= 2 << class products) stay unmapped
     int mapCtaMin = NUM_WARP_SORT;        // first lane-group class whose mapped numeric phase uses the CTA kernel (NUM_WARP_SORT = never)
     u32 partRowCost = 0, partEntryCost = 0;   // partition_rows: cost of a row = products + partEntryCost * entries + partRowCost
+    const void *hubKeyPtr = nullptr;   // A of the last multiply (row_offsets pointer, rows, nnz) and whether it had hub rows:
+    size_t hubKeyRows = 0, hubKeyNnz = 0;   // the queue + k_analyze_long launch is skipped for a matrix known to have none
+    bool hubRows = true;
     int tieredAnalysis = 0;   // 1: two-pass analysis (row_offsets pairs first, column extents only for rows that use them);
                               // measured slower even when B's 16-byte row summaries miss the L2 (R-MAT scale 24: analysis
                               // 1.70 -> 1.97 ms), so it is off; kept as a tested option
-    bool deterministic = false;   // bit-reproducible values in the oracle's summation order (slower): sort classes
+    bool deterministic = false;   // bit-reproducible values in sequential ascending-k summation order (slower): sort classes
                               // up to 8192 products, sequential-k kernel for every local bitmap row that fits, the
                               // remaining bitmap rows recomputed by k_det_rows
     int denseSeq = 1;         // banded / high-compression rows: sequential-k numeric kernel (dense_seq.cuh): 0 = off,
@@ -251,17 +254,22 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // B-row summaries: 16 B per row of B, one gather per A entry (option tiered_analysis = 1: row_offsets pairs only,
     // column extents in a second pass for the rows that use them)
     const bool tiered = c->tieredAnalysis == 1;
+    // hub rows of A (>= 1024 entries) are queued for one CTA each; a matrix seen before without any skips that launch
+    const bool sameA = c->hubKeyPtr == (const void *)aRp && c->hubKeyRows == A->rows && c->hubKeyNnz == A->nnz;
+    const bool useHubQueue = !sameA || c->hubRows;
     if (!tiered) launch_row_info(lc, (u32)B->rows, bRp, bCi, (uint4 *)c->rowInfo.p);
     launch_analyze(lc, rows, A->nnz, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, cRp, c->dSc, sortMax,
                    wantMap ? (uint2 *)c->aSeg.p : nullptr, tiered ? nullptr : (const uint4 *)c->rowInfo.p,
                    wantMap && c->segNum ? (u32 *)c->aOff.p : nullptr, wantMap ? (u32 *)c->mapLen.p : nullptr, useRank,
-                   c->mapMinClass, tiered ? min(128u, sortMax + 1u) : 0u);
+                   c->mapMinClass, tiered ? min(128u, sortMax + 1u) : 0u, useHubQueue ? perm /* free until k_bin_scatter */ : nullptr);
     if (wantMap) launch_scan_map(lc, (const u32 *)c->mapLen.p, (u64 *)c->mapBase.p, rows + 1, (u64 *)c->tileState.p, c->dSc);
     launch_bin_scatter(lc, rows, aRp, rowOps, rowMin, rowMax, perm, c->dSc, sortMax, wantMap ? (const u64 *)c->mapBase.p : nullptr,
                        wantMap ? (RowDesc *)c->desc.p : nullptr);
     cudaEventRecord(c->evStage[1], c->main);
     if ((rc = read_scalars(c, lc))) return rc;
     const Scalars s1 = *c->hSc;
+    c->hubKeyPtr = aRp; c->hubKeyRows = A->rows; c->hubKeyNnz = A->nnz;
+    if (useHubQueue) c->hubRows = s1.longCount != 0;
     if (s1.products == 0) {  // Multiply.cu:256-261: alloc(rows, cols, 0, false)
         if (C->data) cudaFree(C->data);
         if (C->col_ids) cudaFree(C->col_ids);

@@ -50,6 +50,7 @@ struct Scalars {
     u32 tileCounter;          // dynamic tile ids of the row_ptr scan
     u32 mapTileCounter;       // dynamic tile ids of the rank-map offset scan
     u64 mapTotal;             // entries of the rank map (products of all mapped rows)
+    u32 longCount;            // hub rows of A queued by k_analyze for k_analyze_long
     u32 seqRows[2];           // local bitmap rows the sequential-k numeric kernel takes (<= 512 / <= 2048 entries), counted
                               // by the symbolic kernel so that the host launches those kernels only when needed
     u32 compareFlag;          // k_compare: 0 = equal
@@ -104,7 +105,9 @@ void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, con
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
                     uint2 *aSeg, const uint4 *rowInfo, u32 *aOff = nullptr, u32 *mapLen = nullptr, bool mapCta = false,
                     int mapMinClass = 0, u32 extentMinOps = 0 /* > 0 and no rowInfo: column extents only for rows with at
-                    least this many products (two-pass analysis for matrices whose B summaries would miss the L2) */);
+                    least this many products (two-pass analysis for matrices whose B summaries would miss the L2) */,
+                    u32 *longRows = nullptr /* scratch of `rows` entries: queue of the hub rows of A (>= 1024 entries), which
+                    one CTA each analyses afterwards */);
 // rowInfo[k] = (begin, end, first column, last column) of B row k: one gather per A entry in the analysis
 void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *bCi, uint4 *rowInfo);
 // descriptors (written by launch_bin_scatter, symbolic flavour: c0/c1 = column extent) switched to the numeric
@@ -203,7 +206,7 @@ void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 
                                          +4: rows of <= 512 entries exist, +8: rows of 513..2048 entries exist,
                                          +16: deterministic mode (every row that fits the accumulator) */,
                           const u32 *rowOps = nullptr /* products per row: the sequential-k kernel takes the rows that fold */);
-// deterministic mode: values of the rows of a bitmap bin recomputed in the oracle's order (dense_seq.cuh: k_det_rows);
+// deterministic mode: values of the rows of a bitmap bin recomputed in sequential ascending-k order (dense_seq.cuh: k_det_rows);
 // skipSeqRows: rows the sequential-k kernel wrote are left alone
 template <typename T>
 void launch_det_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi, const T *aV,

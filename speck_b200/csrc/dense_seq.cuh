@@ -10,7 +10,7 @@
 //   * the columns of one B row are distinct, so the lanes of a step never touch the same accumulator:
 //     plain shared-memory read-modify-write, no atomics;
 //   * the order of additions per entry of C is ascending k with separately rounded products (__dmul_rn /
-//     __dadd_rn) -- the CPU oracle's order, so these rows are bit-reproducible and bit-equal to the oracle;
+//     __dadd_rn) -- the order of a sequential Gustavson loop, so these rows are bit-reproducible;
 //   * the B-row segments (columns and values) are staged into a shared-memory ring by bulk asynchronous copies
 //     (cp.async.bulk + mbarrier, issued by one lane, RING segments ahead of the consumer), which is what the
 //     B segments of these matrices suit: tens to hundreds of contiguous entries each.  Segments are fetched as
@@ -282,7 +282,7 @@ void launch_dense_seq_t(const LaunchCtx &lc, const u32 *perm, u32 count, const u
 // ------------------------------------------------------------------------------------------------
 // Deterministic mode (option "deterministic"; the reference is "not bit stable", config.ini:8-9): values of the
 // rows whose numeric kernel accumulates with atomics (rows beyond the sort classes, wide bitmap rows) are
-// recomputed in the oracle's order.  The columns of the row are already in C (sorted); one CTA walks the A entries
+// recomputed in sequential ascending-k order.  The columns of the row are already in C (sorted); one CTA walks the A entries
 // in ascending k, the products of one B row go to distinct entries of C (found by binary search), so every step is
 // a plain read-modify-write; products are rounded before they are added.  Slow (a barrier per A entry), used
 // for the few rows no deterministic kernel takes.

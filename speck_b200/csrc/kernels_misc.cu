@@ -35,6 +35,21 @@ void launch_row_info(const LaunchCtx &lc, u32 rowsB, const u32 *bRp, const u32 *
     ++*lc.launches;
 }
 
+// B-row summary of one A entry: (begin, end, first column, last column); empty rows carry (0xffffffff, 0)
+__device__ __forceinline__ uint4 fetch_row_summary(const uint4 *__restrict__ rowInfo, const u32 *__restrict__ bRp,
+                                                   const u32 *__restrict__ bCi, u32 k, bool tiered)
+{
+    if (rowInfo) return __ldg(rowInfo + k);
+    uint4 ri = make_uint4(__ldg(bRp + k), __ldg(bRp + k + 1), 0xffffffffu, 0u);
+    if (!tiered && ri.y > ri.x) {
+        ri.z = __ldg(bCi + ri.x);
+        ri.w = __ldg(bCi + ri.y - 1);
+    }
+    return ri;
+}
+
+constexpr u32 ANALYZE_LONG_ROW = 1024;   // A rows with at least this many entries: one CTA per row (k_analyze_long)
+
 template <int LA>
 __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict__ aRp,
                                                  const u32 *__restrict__ aCi,
@@ -44,7 +59,7 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
                                                  u32 sortMax, uint2 *__restrict__ aSeg,
                                                  const uint4 *__restrict__ rowInfo, u32 *__restrict__ aOff,
                                                  u32 *__restrict__ mapLen, bool mapCta, int mapMinClass,
-                                                 u32 extentMinOps)
+                                                 u32 extentMinOps, u32 *__restrict__ longRows)
 {
     __shared__ u32 sBin[NUM_BINS];
     __shared__ unsigned long long sProd;
@@ -61,23 +76,22 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
     u32 cmin = 0xffffffffu, cmax = 0u;  // column extent of the row's products: B rows are sorted, so the
                                         // first / last entry of each referenced B row bound it (the
                                         // reference's rowColMinMax, common.cuh:395-400)
-    const u32 beg = row < rows ? aRp[row] : 0u, end = row < rows ? aRp[row + 1] : 0u;
+    u32 beg = row < rows ? aRp[row] : 0u, end = row < rows ? aRp[row + 1] : 0u;
     aLen = end - beg;
+    // hub rows of A (web graphs: thousands of entries) would serialise hundreds of dependent gathers on one lane
+    // group: they are queued for k_analyze_long (one CTA per row) and skipped here
+    const bool queued = longRows && aLen >= ANALYZE_LONG_ROW;
+    if (queued) {
+        if (lane == 0) longRows[atomicAdd(&sc->longCount, 1u)] = row;
+        end = beg;
+    }
     // B-row summary of one A entry: (begin, end, first column, last column); empty rows carry (0xffffffff, 0)
     // extentMinOps > 0 (no rowInfo table: B has so many rows that the 16-byte summaries would miss the L2): the first
     // pass gathers only the row_offsets pair (4 B per row of B, L2-resident); the first / last columns are gathered in a
     // second pass for the rows with at least extentMinOps products -- the only ones whose extent is ever used
     // (banded test of classify_row, rank and bitmap kernels); the others keep the placeholder extent [0, 0].
     const bool tiered = !rowInfo && extentMinOps > 0;
-    auto fetch = [&](u32 k) -> uint4 {
-        if (rowInfo) return __ldg(rowInfo + k);
-        uint4 ri = make_uint4(__ldg(bRp + k), __ldg(bRp + k + 1), 0xffffffffu, 0u);
-        if (!tiered && ri.y > ri.x) {
-            ri.z = __ldg(bCi + ri.x);
-            ri.w = __ldg(bCi + ri.y - 1);
-        }
-        return ri;
-    };
+    auto fetch = [&](u32 k) -> uint4 { return fetch_row_summary(rowInfo, bRp, bCi, k, tiered); };
     const u32 gmask = LA == 32 ? 0xffffffffu : (((1u << (LA & 31)) - 1u) << ((threadIdx.x & 31) - lane));
     if (!aOff) {
         // four entries per lane and iteration: their summary gathers are in flight together (a hub row of A
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
 
     u64 myProd = 0;
     u32 myMax = 0;
-    if (row < rows && lane == 0) {
+    if (row < rows && lane == 0 && !queued) {
         rowOps[row] = ops;
         rowMin[row] = cmin;
         rowMax[row] = cmax;
@@ -196,10 +210,86 @@ __global__ void __launch_bounds__(256) k_analyze(u32 rows, const u32 *__restrict
     }
 }
 
+// One CTA per queued hub row of A: same outputs as k_analyze, 1024 entries per iteration.
+__global__ void __launch_bounds__(256) k_analyze_long(const u32 *__restrict__ longRows, const u32 *__restrict__ aRp,
+                                                      const u32 *__restrict__ aCi, const u32 *__restrict__ bRp,
+                                                      const u32 *__restrict__ bCi, u32 *__restrict__ rowOps,
+                                                      u32 *__restrict__ rowMin, u32 *__restrict__ rowMax,
+                                                      u32 *__restrict__ rowNnz, Scalars *sc, u32 sortMax,
+                                                      uint2 *__restrict__ aSeg, const uint4 *__restrict__ rowInfo,
+                                                      u32 *__restrict__ mapLen, bool mapCta, int mapMinClass, u32 extentMinOps)
+{
+    __shared__ unsigned long long sOps[8];
+    __shared__ u32 sMin[8], sMax[8];
+    const u32 n = sc->longCount;
+    for (u32 i = blockIdx.x; i < n; i += gridDim.x) {
+        const u32 row = longRows[i];
+        const u32 beg = aRp[row], end = aRp[row + 1];
+        u64 ops64 = 0;
+        u32 cmin = 0xffffffffu, cmax = 0u;
+        for (u32 p0 = beg + threadIdx.x; p0 < end; p0 += 4 * 256) {
+            u32 kk[4];
+            uint4 ri[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = (p0 + u * 256 < end) ? __ldg(aCi + p0 + u * 256) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ri[u] = make_uint4(0u, 0u, 0xffffffffu, 0u);
+                if (kk[u] != 0xffffffffu) {
+                    ri[u] = fetch_row_summary(rowInfo, bRp, bCi, kk[u], false);   // a hub row always needs its extent
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kk[u] == 0xffffffffu) continue;
+                cmin = min(cmin, ri[u].z);
+                cmax = max(cmax, ri[u].w);
+                ops64 += (u64)(ri[u].y - ri[u].x);
+                if (aSeg) aSeg[p0 + u * 256] = make_uint2(ri[u].x, ri[u].y);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            ops64 += __shfl_xor_sync(0xffffffffu, ops64, d);
+            cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, d));
+            cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+        }
+        __syncthreads();   // the arrays may still be read by thread 0 of the previous row
+        if ((threadIdx.x & 31) == 0) {
+            sOps[threadIdx.x >> 5] = ops64;
+            sMin[threadIdx.x >> 5] = cmin;
+            sMax[threadIdx.x >> 5] = cmax;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                ops64 += sOps[w];
+                cmin = min(cmin, sMin[w]);
+                cmax = max(cmax, sMax[w]);
+            }
+            const u32 ops = ops64 > 0xffffffffull ? 0xffffffffu : (u32)ops64;
+            rowOps[row] = ops;
+            rowMin[row] = cmin;
+            rowMax[row] = cmax;
+            const int bin = classify_row(ops, end - beg, ops ? cmax - cmin + 1u : 0u, sortMax);
+            if (mapLen) {
+                const bool mapped = bin >= BIN_SORT0 + mapMinClass && (bin < BIN_SORT0 + NUM_WARP_SORT || (mapCta && bin < BIN_DENSE_LOCAL));
+                mapLen[row] = mapped ? ops : 0u;
+            }
+            if (bin < 0)
+                rowNnz[row] = 0;
+            else
+                atomicAdd(&sc->binCount[bin], 1u);
+            if (ops64) atomicAdd((unsigned long long *)&sc->products, (unsigned long long)ops64);
+            if (ops) atomicMax(&sc->maxRowProducts, ops);
+        }
+    }
+}
+
 void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, const u32 *aCi, const u32 *bRp,
                     const u32 *bCi, u32 *rowOps, u32 *rowMin, u32 *rowMax, u32 *rowNnz, Scalars *sc, u32 sortMax,
                     uint2 *aSeg, const uint4 *rowInfo, u32 *aOff, u32 *mapLen, bool mapCta, int mapMinClass,
-                    u32 extentMinOps)
+                    u32 extentMinOps, u32 *longRows)
 {
     if (rows == 0) return;
     const double avg = (double)nnzA / (double)rows;
@@ -207,13 +297,18 @@ void launch_analyze(const LaunchCtx &lc, u32 rows, u64 nnzA, const u32 *aRp, con
 #define SB_ANALYZE(LA)                                                                                                     \
     k_analyze<LA><<<(u32)(((u64)rows * LA + threads - 1) / threads), threads, 0, lc.stream>>>(                             \
         rows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax, aSeg, rowInfo, aOff, mapLen, mapCta, mapMinClass,  \
-        extentMinOps)
+        extentMinOps, aOff ? nullptr : longRows)
     if (avg <= 3.0) SB_ANALYZE(2);
     else if (avg <= 6.0) SB_ANALYZE(4);
     else if (avg <= 24.0) SB_ANALYZE(8);
     else SB_ANALYZE(32);
 #undef SB_ANALYZE
     ++*lc.launches;
+    if (longRows && !aOff) {   // the queue is usually empty: the CTAs read one counter and leave
+        k_analyze_long<<<lc.smCount, 256, 0, lc.stream>>>(longRows, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax, rowNnz, sc, sortMax,
+                                                          aSeg, rowInfo, mapLen, mapCta, mapMinClass, extentMinOps);
+        ++*lc.launches;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

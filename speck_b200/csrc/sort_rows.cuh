@@ -12,7 +12,7 @@
 //            sort (reference :715-728, :837-850).
 //   emit   : symbolic -> number of distinct columns; numeric -> heads of equal-column runs are
 //            ranked with ballot/popc, the run's products are added in ascending p (= ascending k,
-//            the CPU oracle's order) and (col, val) is written to consecutive positions of C.
+//            the order of a sequential Gustavson loop) and (col, val) is written to consecutive positions of C.
 #pragma once
 #include "common.cuh"
 

@@ -668,3 +668,22 @@ def test_tiered_analysis(ctx, sort_max_value):
     finally:
         ctx.set_option("tiered_analysis", 0)
         ctx.set_option("sort_max", 16384)
+
+
+def test_hub_rows_of_a_take_the_cta_analysis(ctx, sort_max):
+    """A rows with >= 1024 entries are analysed by one CTA each (k_analyze_long); mixed with ordinary and empty rows,
+    hub rows referencing empty and long B rows."""
+    rng = np.random.default_rng(8)
+    n = 6000
+    r = list(rng.integers(0, n, 20000))
+    c = list(rng.integers(0, n, 20000))
+    for hub, cnt in ((5, 1024), (77, 1023), (4000, 3000), (5999, 5500)):
+        cols = rng.choice(n, cnt, replace=False)
+        r += [hub] * cnt
+        c += list(cols)
+    keep = [i for i in range(len(r)) if c[i] % 11 != 3]      # every 11th B row (= A row here) stays empty
+    A = M.from_coo(n, n, np.array(r)[keep], np.array(c)[keep], seed=9)
+    lens = np.diff(A.row_offsets.astype(np.int64))
+    assert (lens >= 1024).sum() >= 2
+    got, st = check_case(ctx, A, what=f"hub rows sort_max={sort_max}")
+    assert st["max_row_products"] >= 5000
