@@ -49,4 +49,18 @@ with api.Context(0) as ctx:
     ctx.set_option("deterministic", 1)
     check(ctx, M.rmat(13, 16, seed=13), what="deterministic mode")
     ctx.set_option("deterministic", 0)
+    # hub rows of A (k_analyze_long) and the GPU-side COO -> CSR
+    rng = np.random.default_rng(8)
+    n = 4000
+    r = list(rng.integers(0, n, 12000)) + [7] * 1500 + [3999] * 2500
+    c = list(rng.integers(0, n, 12000)) + list(rng.choice(n, 1500, replace=False)) + list(rng.choice(n, 2500, replace=False))
+    H = M.from_coo(n, n, np.array(r), np.array(c), seed=9)
+    check(ctx, H, what="hub rows of A")
+    d = ctx.coo_to_csr(n, n, np.array(r, np.uint32), np.array(c, np.uint32), rng.standard_normal(len(r)), sum_duplicates=True)
+    h = ctx.download(d)
+    assert h.nnz == H.nnz and np.array_equal(h.col_ids, H.col_ids), "coo_to_csr"
+    d.free()
+    print("ok GPU COO -> CSR", flush=True)
+    eq, mm = ctx.compare_report(ctx.upload(H), ctx.upload(H), True)
+    assert eq
 print("all ok")
