@@ -218,6 +218,8 @@ int speck_b200_sharded_destroy(speck_shard_plan *plan);
  *                       (rank_flat.cuh), 0: register-slot variant (rank_cta.cuh); "flat_e" 8 / 16 slots per thread
  *   "dense_seq"         banded / high-compression rows: 1 (default) sequential-k numeric kernel with lane loads,
  *                       2: the same with TMA (cp.async.bulk) staged B segments, 0: product-parallel kernel only
+ *   "test_set"          1 (default): the symbolic bitmap kernel of the banded / high-compression rows reads the bitmap
+ *                       word before its atomicOr (most bits are set already when many products fold into a column)
  *   "deterministic"     1: values bit-reproducible, summed in sequential order (ascending k, products
  *                       rounded before they are added); slower: no rank map, sort classes, rows that accumulate
  *                       with atomics are recomputed.  Default 0 (like the reference: "not bit stable")

@@ -93,6 +93,7 @@ struct speck_ctx {
     bool deterministic = false;   // bit-reproducible values in sequential ascending-k summation order (slower): sort classes
                               // up to 8192 products, sequential-k kernel for every local bitmap row that fits, the
                               // remaining bitmap rows recomputed by k_det_rows
+    bool testSet = true;      // local bitmap rows, symbolic: read the bitmap word before the atomicOr
     int denseSeq = 1;         // banded / high-compression rows: sequential-k numeric kernel (dense_seq.cuh): 0 = off,
                               // 1 = B segments loaded by the lanes, 2 = staged by TMA bulk copies
     int colDirect = 0;        // mapped numeric CTA kernels: 1..3 = the large shapes stage values only and write column ids
@@ -323,7 +324,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         launch_dense_symbolic(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[loc], aRp,
                               aCi, bRp, bCi, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp,
-                              rowOps, (loc && (c->denseSeq || det)) ? c->dSc->seqRows : nullptr, det);
+                              rowOps, (loc && (c->denseSeq || det)) ? c->dSc->seqRows : nullptr, det, loc && c->testSet);
     }
     // rank classes: the CTA sort bins grouped by launch shape (products <= 8192 / 4096 / 2048 / 1024)
     if (useRank) {
@@ -1181,6 +1182,10 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     }
     if (!strcmp(key, "deterministic")) {
         c->deterministic = value != 0;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "test_set")) {
+        c->testSet = value != 0;
         return SPECK_OK;
     }
     if (!strcmp(key, "dense_seq")) {

@@ -195,7 +195,8 @@ void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32
                            const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB,
                            const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz,
                            const u32 *rowOps = nullptr, u32 *seqRows = nullptr /* Scalars::seqRows, counted for local rows */,
-                           bool everyRow = false /* deterministic mode: count every row that fits, whatever its fold */);
+                           bool everyRow = false /* deterministic mode: count every row that fits, whatever its fold */,
+                           bool testSet = false /* local rows: read the bitmap word before the atomicOr */);
 size_t dense_local_store_bytes(u32 count);
 template <typename T>
 void launch_dense_numeric(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,

@@ -87,7 +87,8 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
              const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
              const u32 *__restrict__ bCi, const T *__restrict__ bV, const int winBits,
              const u32 *__restrict__ rowMin, const u32 *__restrict__ rowMax, u32 *bitmapStore, u32 *cRp,
-             u32 *__restrict__ cCi, T *cV, const u32 seqMax, const u32 *__restrict__ rowOps, u32 *seqRows, const u32 fold)
+             u32 *__restrict__ cCi, T *cV, const u32 seqMax, const u32 *__restrict__ rowOps, u32 *seqRows, const u32 fold,
+             const bool testSet)
 {
     extern __shared__ __align__(16) u32 dsm[];
     const u32 W = 1u << winBits;
@@ -208,8 +209,13 @@ k_dense_rows(const u32 *__restrict__ perm, const u32 count, u32 *rowCounter, con
                         for (int u = 0; u < 4; ++u) {
                             if (q[u] != 0xffffffffu) {
                                 const u32 c = cc[u] - winLo;
-                                atomicOr(&bitmap[c >> 5], 1u << (c & 31));
-                                touched[c >> 7] = 1;
+                                // test before set: in rows that fold (FEM-like: ~18 products per column) most bits are
+                                // set already and a plain shared load is far cheaper than the atomic (option test_set)
+                                const u32 bit = 1u << (c & 31);
+                                if (!testSet || !(bitmap[c >> 5] & bit)) {
+                                    atomicOr(&bitmap[c >> 5], bit);
+                                    touched[c >> 7] = 1;
+                                }
                             }
                         }
                     }
@@ -338,7 +344,8 @@ template <int THREADS, typename T, bool NUMERIC, int SVALS>
 static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u32 count, u32 *rowCounter,
                            const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi, const T *bV,
                            const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *cRp, u32 *cCi, T *cV,
-                           u32 seqMax = 0, const u32 *rowOps = nullptr, u32 *seqRows = nullptr, u32 fold = DENSE_SEQ_FOLD)
+                           u32 seqMax = 0, const u32 *rowOps = nullptr, u32 *seqRows = nullptr, u32 fold = DENSE_SEQ_FOLD,
+                           bool testSet = false)
 {
     const size_t smem = dense_smem_bytes(winBits, THREADS, sizeof(T)) + (size_t)SVALS * sizeof(T);
     auto kern = k_dense_rows<THREADS, T, NUMERIC, SVALS>;
@@ -349,7 +356,7 @@ static void launch_dense_t(const LaunchCtx &lc, int winBits, const u32 *perm, u3
     u32 grid = (u32)(lc.smCount * perSm);
     if (grid > count) grid = count;
     kern<<<grid, THREADS, smem, lc.stream>>>(perm, count, rowCounter, aRp, aCi, aV, bRp, bCi, bV, winBits, rowMin,
-                                             rowMax, bitmapStore, cRp, cCi, cV, seqMax, rowOps, seqRows, fold);
+                                             rowMax, bitmapStore, cRp, cCi, cV, seqMax, rowOps, seqRows, fold, testSet);
     ++*lc.launches;
 }
 
@@ -363,7 +370,7 @@ size_t dense_local_store_bytes(u32 count) { return (size_t)count * ((size_t)1 <<
 void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32 count, u32 *rowCounter,
                            const u32 *aRp, const u32 *aCi, const u32 *bRp, const u32 *bCi, u32 colsB,
                            const u32 *rowMin, const u32 *rowMax, u32 *bitmapStore, u32 *rowNnz, const u32 *rowOps,
-                           u32 *seqRows, bool everyRow)
+                           u32 *seqRows, bool everyRow, bool testSet)
 {
     if (count == 0) return;
     const float *nv = nullptr;
@@ -371,7 +378,7 @@ void launch_dense_symbolic(const LaunchCtx &lc, bool local, const u32 *perm, u32
         launch_dense_t<256, float, false, 0>(lc, DENSE_LOCAL_BITS, perm, count, rowCounter, aRp, aCi, nv, bRp, bCi, nv,
                                              rowMin, rowMax, bitmapStore, rowNnz, nullptr, nullptr, 0u,
                                              rowOps, (bitmapStore && rowOps) ? seqRows : nullptr,
-                                             everyRow ? 0u : DENSE_SEQ_FOLD);
+                                             everyRow ? 0u : DENSE_SEQ_FOLD, testSet);
     else
         launch_dense_t<1024, float, false, 0>(lc, dense_window_bits(colsB), perm, count, rowCounter, aRp, aCi, nv, bRp,
                                               bCi, nv, rowMin, rowMax, nullptr, rowNnz, nullptr, nullptr, 0u, rowOps);

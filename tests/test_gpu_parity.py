@@ -640,6 +640,16 @@ def test_deterministic_mode_is_bit_equal_to_the_oracle(ctx):
     check_case(ctx, cases[0][1], what="default after deterministic")
 
 
+def test_dense_symbolic_without_test_before_set(ctx):
+    """test_set = 0: the bitmap pass sets every bit with an atomicOr (the default reads the word first)."""
+    ctx.set_option("test_set", 0)
+    try:
+        check_case(ctx, M.fem3d_like(9, 8, 7), what="fem, test_set=0")
+        check_case(ctx, M.banded_fem_like(n=4000, per_row=64, clusters=8, band=300, seed=41), what="banded, test_set=0")
+    finally:
+        ctx.set_option("test_set", 1)
+
+
 def test_col_direct_variants(ctx):
     """col_direct = 1..3: the large mapped numeric shapes write column ids straight to C (kept as a tested option)."""
     A = M.rmat(15, 16, seed=15)
