@@ -46,7 +46,8 @@ int fail(int code, const char *fmt, ...)
                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int NSIDE = 4;
+constexpr int NSIDE = 4;      // side streams of the default launch plan
+constexpr int NSTREAMS = 8;   // ... plus four that only the "sym_mix" plan forks
 
 struct DevBuf {
     void *p = nullptr;
@@ -59,8 +60,8 @@ struct speck_ctx {
     int device = 0;
     int smCount = 0;
     cudaStream_t main = nullptr;
-    cudaStream_t side[NSIDE] = {};
-    cudaEvent_t evFork = nullptr, evJoin[NSIDE] = {};
+    cudaStream_t side[NSTREAMS] = {};
+    cudaEvent_t evFork = nullptr, evJoin[NSTREAMS] = {};
     cudaEvent_t evStage[6] = {};
     Scalars *dSc = nullptr;
     Scalars *hSc = nullptr;  // pinned, mapped: written by k_publish (or by a plain D2H copy when spinWait is off)
@@ -96,6 +97,13 @@ struct speck_ctx {
     bool testSet = true;      // local bitmap rows, symbolic: read the bitmap word before the atomicOr
     int denseSeq = 1;         // banded / high-compression rows: sequential-k numeric kernel (dense_seq.cuh): 0 = off,
                               // 1 = B segments loaded by the lanes, 2 = staged by TMA bulk copies
+    int flatMinClass = NUM_WARP_SORT;   // lane-group classes >= this (6 = 256, 7 = 512 products) rank with the flat bitmap
+                              // kernel instead of the register bitonic sort (mapped, two-level matrices only)
+    int symMix = 0;           // symbolic phase: > 0 = the lane-group sort kernels of the 128 / 256 / 512-product classes
+                              // (instruction-bound) run with about this many CTAs per SM, looping over their rows, next
+                              // to the bitmap rank kernels (shared-memory-bound) instead of after them
+    int bigSplit = 0;         // mapped numeric kernel of rows of 4097 .. 16384 products: 1..3 = several CTAs per row
+                              // (map_split.cuh), 0 = one 1024-thread CTA per row
     int colDirect = 0;        // mapped numeric CTA kernels: 1..3 = the large shapes stage values only and write column ids
                               // straight to C (rank_cta.cuh: COLDIRECT); measured slower (profiles/r2_notes.md), off
     int segNum = 0;           // mapped numeric CTA classes: 1 = segment-major kernel (map_seg.cuh; measured slower: fewer
@@ -171,15 +179,15 @@ int read_scalars(speck_ctx *c, LaunchCtx &lc)
     return SPECK_OK;
 }
 
-void fork_streams(speck_ctx *c)
+void fork_streams(speck_ctx *c, int n = NSIDE)
 {
     cudaEventRecord(c->evFork, c->main);
-    for (int i = 0; i < NSIDE; ++i) cudaStreamWaitEvent(c->side[i], c->evFork, 0);
+    for (int i = 0; i < n; ++i) cudaStreamWaitEvent(c->side[i], c->evFork, 0);
 }
 
-void join_streams(speck_ctx *c)
+void join_streams(speck_ctx *c, int n = NSIDE)
 {
-    for (int i = 0; i < NSIDE; ++i) {
+    for (int i = 0; i < n; ++i) {
         cudaEventRecord(c->evJoin[i], c->side[i]);
         cudaStreamWaitEvent(c->main, c->evJoin[i], 0);
     }
@@ -316,8 +324,29 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         }
     }
     // ---- symbolic: dense rows first (longest), then the sort classes from large to small
-    fork_streams(c);
+    const bool mix = c->symMix > 0 && useRank && desc && rankLevels == 2;
+    const int symForked = mix ? NSTREAMS : NSIDE;
+    fork_streams(c, symForked);
     int sidx = 0;
+    bool sortDone[NUM_SORT] = {};
+    if (mix) {
+        // "sym_mix": the three largest lane-group classes first, each on its own stream with a capped grid (shares of
+        // sym_mix CTAs per SM in proportion to their products), so that the rank kernels launched next fill the rest of
+        // every SM: the bitonic sort is bound by instruction issue, the bitmap kernels by the shared-memory pipe
+        u64 work[NUM_WARP_SORT] = {}, total = 0;
+        for (int sc = NUM_WARP_SORT - 3; sc < NUM_WARP_SORT; ++sc)
+            if (sc >= c->mapMinClass) total += work[sc] = (u64)s1.binCount[BIN_SORT0 + sc] << (sc + 2);
+        for (int sc = NUM_WARP_SORT - 1; sc >= NUM_WARP_SORT - 3 && total; --sc) {
+            const u32 cnt = s1.binCount[BIN_SORT0 + sc];
+            if (!cnt || !work[sc] || (rankLevels == 3 && sort_keys_wide(sc, colsB))) continue;
+            LaunchCtx ls{c->side[NSIDE + (NUM_WARP_SORT - 1 - sc)], c->smCount, &c->launches};
+            const u64 share = ((u64)c->smCount * (u64)c->symMix * work[sc] + total - 1) / total;
+            ls.gridCap = (u32)max((u64)c->smCount, share);
+            launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
+                                 rowOps, cRp, desc + binStart[BIN_SORT0 + sc], aSeg, rankMap);
+            sortDone[sc] = true;
+        }
+    }
     for (int loc = 0; loc < 2; ++loc) {
         const int bin = loc ? BIN_DENSE_LOCAL : BIN_DENSE;
         if (!s1.binCount[bin]) continue;
@@ -349,7 +378,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     }
     for (int sc = (useRank ? NUM_WARP_SORT : NUM_SORT) - 1; sc >= 0; --sc) {
         const u32 cnt = s1.binCount[BIN_SORT0 + sc];
-        if (!cnt) continue;
+        if (!cnt || sortDone[sc]) continue;
         LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         const bool mapped = desc && sc >= c->mapMinClass;
         // 64-bit sort keys cost 2-3x (R-MAT scale 24: 28 ps per product in the 512 class): wide matrices rank these
@@ -357,11 +386,14 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (mapped && useRank && rankLevels == 3 && sc >= 6 && sc < NUM_WARP_SORT && sort_keys_wide(sc, colsB))
             launch_rank_symbolic(ls, 4u << sc, perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi, rowOps, rowMin, rowMax,
                                  cRp, desc + binStart[BIN_SORT0 + sc], aSeg, rankMap, 3);
+        else if (mapped && useRank && rankLevels == 2 && c->flatSym && sc >= c->flatMinClass && sc >= 6)
+            // 129..512 products: the flat bitmap kernel on 32 / 64 threads instead of the register bitonic sort
+            launch_rank_flat(ls, 4u << sc, 8, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, bCi, rankMap, cRp);
         else
             launch_sort_symbolic(ls, sc, sort_keys_wide(sc, colsB), perm + binStart[BIN_SORT0 + sc], cnt, aRp, aCi, bRp, bCi,
                                  rowOps, cRp, mapped ? desc + binStart[BIN_SORT0 + sc] : nullptr, aSeg, rankMap);
     }
-    join_streams(c);
+    join_streams(c, symForked);
     CU_TRY(cudaGetLastError());   // launch / attribute errors of the symbolic kernels (side streams are joined)
     cudaEventRecord(c->evStage[2], c->main);
 
@@ -426,7 +458,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             if (rankMap && c->segNum)
                 launch_map_seg<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, (const u32 *)c->aOff.p, aV, bCi, bV, rankMap, cCi, cV);
             else if (rankMap)
-                launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV, c->colDirect);
+                launch_map_numeric_cta<T>(ls, 1024u << g, desc + binStart[b0], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV, c->colDirect, c->bigSplit);
             else if (rankLevels == 2)
                 launch_rank_numeric<T>(ls, 1024u << g, perm + binStart[b0], cnt, aRp, aCi, aV, bRp, bCi, bV, rowOps, rowMin,
                                        rowMax, cRp, cCi, cV);
@@ -657,7 +689,7 @@ int speck_b200_create(int device, speck_ctx **out)
     // synchronisation.  The side streams only ever run between a fork from and a join into the main stream.
     const int rc = [&]() -> int {
         CU_TRY(cudaStreamCreate(&c->main));
-        for (int i = 0; i < NSIDE; ++i) {
+        for (int i = 0; i < NSTREAMS; ++i) {
             CU_TRY(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
             CU_TRY(cudaEventCreateWithFlags(&c->evJoin[i], cudaEventDisableTiming));
         }
@@ -694,7 +726,7 @@ int speck_b200_destroy(speck_ctx *c)
     if (c->dSc) cudaFree(c->dSc);
     if (c->hSc) cudaFreeHost(c->hSc);
     for (auto &e : c->evStage) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < NSIDE; ++i) {
+    for (int i = 0; i < NSTREAMS; ++i) {
         if (c->evJoin[i]) cudaEventDestroy(c->evJoin[i]);
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
     }
@@ -1196,6 +1228,21 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "col_direct")) {
         if (value < 0 || value > 3) return fail(SPECK_ERR_INVALID, "col_direct must be in [0, 3]");
         c->colDirect = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "flat_min_class")) {
+        if (value < 6 || value > NUM_WARP_SORT) return fail(SPECK_ERR_INVALID, "flat_min_class must be in [6, %d]", NUM_WARP_SORT);
+        c->flatMinClass = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "sym_mix")) {
+        if (value < 0 || value > 16) return fail(SPECK_ERR_INVALID, "sym_mix must be in [0, 16]");
+        c->symMix = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "big_split")) {
+        if (value < 0 || value > 3) return fail(SPECK_ERR_INVALID, "big_split must be in [0, 3]");
+        c->bigSplit = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "spin_wait")) {

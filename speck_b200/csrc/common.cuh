@@ -95,6 +95,8 @@ struct LaunchCtx {
     cudaStream_t stream;
     int smCount;
     u32 *launches;   // incremented per kernel launch
+    u32 gridCap = 0; // lane-group sort kernels: at most this many CTAs, each looping over row groups (0: one CTA per group
+                     // of rows); lets a long instruction-bound kernel share the SMs with kernels of other streams
 };
 
 // aOff (optional, nnz(A) entries): index of every A entry's first product in its row's flat product enumeration
@@ -154,7 +156,8 @@ template <typename T>
 void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
                             const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi,
                             T *cV, int colDirect = 0 /* 1: the 1024-thread shapes write column ids straight to C and
-                            stage only the values (two CTAs per SM), 2: the 512-thread shape as well */);
+                            stage only the values (two CTAs per SM), 2: the 512-thread shape as well */,
+                            int bigSplit = 0 /* rows of 4097 .. 16384 products: several CTAs per row (map_split.cuh) */);
 template <typename T>
 void launch_sort_numeric(const LaunchCtx &lc, int sortClass, bool wideKeys, const u32 *perm, u32 count,
                          const u32 *aRp, const u32 *aCi, const T *aV, const u32 *bRp, const u32 *bCi,

@@ -17,7 +17,9 @@ void launch_rank_flat(const LaunchCtx &lc, u32 capProducts, int perThread, const
         else if (capProducts <= 8192) SB_FLAT(512, 16);
         else SB_FLAT(1024, 16);
     } else {
-        if (capProducts <= 1024) SB_FLAT(128, 8);
+        if (capProducts <= 256) SB_FLAT(32, 8);         // lane-group classes routed here by "flat_min_class"
+        else if (capProducts <= 512) SB_FLAT(64, 8);
+        else if (capProducts <= 1024) SB_FLAT(128, 8);
         else if (capProducts <= 2048) SB_FLAT(256, 8);
         else if (capProducts <= 4096) SB_FLAT(512, 8);
         else if (capProducts <= 8192) SB_FLAT(1024, 8);

@@ -3,6 +3,7 @@
 // were measured slower on the same rows, profiles/r1_notes.md), and 1024 x 16 for rows of 8193..16384
 // products.  `capProducts` is the largest product count among the rows of the launch.
 #include "rank_cta.cuh"
+#include "map_split.cuh"
 
 namespace sb {
 
@@ -74,9 +75,27 @@ void launch_rank_numeric(const LaunchCtx &lc, u32 capProducts, const u32 *perm, 
 template <typename T>
 void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc *desc, u32 count, const uint2 *aSeg,
                             const T *aV, const u32 *bCi, const T *bV, const unsigned short *rankMap, u32 *cCi,
-                            T *cV, int colDirect)
+                            T *cV, int colDirect, int bigSplit)
 {
     if (count == 0) return;
+#define SB_MAP_SPLIT(TH, E, S) launch_map_rows_split<TH, E, T, S>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
+    // rows of 4097 .. 16384 products: several CTAs per row, each staging one range of the row's positions, instead of
+    // one 1024-thread CTA per SM (map_split.cuh).  1: 512 x 16 slots (two CTAs per SM), the 16384 class split in two;
+    // 2: 512 x 8 slots (three CTAs per SM), split in two / four; 3: only the 16384 class (512 x 16, split in two)
+    if (bigSplit && !colDirect && capProducts > 512 * RANK_E) {
+        const bool top = capProducts > 1024 * RANK_E;
+        if (bigSplit == 1 || (bigSplit == 3 && top)) {
+            if (top) SB_MAP_SPLIT(512, 2 * RANK_E, 2);
+            else launch_map_rows_cta<512, 2 * RANK_E, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV);
+            return;
+        }
+        if (bigSplit == 2) {
+            if (top) SB_MAP_SPLIT(512, RANK_E, 4);
+            else SB_MAP_SPLIT(512, RANK_E, 2);
+            return;
+        }
+    }
+#undef SB_MAP_SPLIT
 #define SB_MAP_NUM(TH, E) launch_map_rows_cta<TH, E, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
 #define SB_MAP_NUM_CD(TH, E) launch_map_rows_cta<TH, E, T, true>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
     if (capProducts <= 32 * RANK_E) SB_MAP_NUM(32, RANK_E);
@@ -95,7 +114,7 @@ void launch_map_numeric_cta(const LaunchCtx &lc, u32 capProducts, const RowDesc 
                                          const u32 *, const u32 *, const T *, const u32 *, const u32 *, const u32 *,   \
                                          const u32 *, u32 *, T *);                                                     \
     template void launch_map_numeric_cta<T>(const LaunchCtx &, u32, const RowDesc *, u32, const uint2 *, const T *,    \
-                                            const u32 *, const T *, const unsigned short *, u32 *, T *, int);
+                                            const u32 *, const T *, const unsigned short *, u32 *, T *, int, int);
 SB_INST(double)
 SB_INST(float)
 #undef SB_INST

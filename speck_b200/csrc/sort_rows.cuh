@@ -114,8 +114,8 @@ struct SortLayout {
 };
 
 template <int G, int E, typename KeyT, typename T, int MODE>
-__global__ void __launch_bounds__(SORT_BLOCK)
-k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
+__device__ __forceinline__ void
+sort_rows_body(const u32 blk, const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
             const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
             const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
             u32 *cRp /* symbolic: counts out; numeric: offsets in */, u32 *__restrict__ cCi,
@@ -139,7 +139,7 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
     T *vals = reinterpret_cast<T *>(smemRaw + ((L::KEY_BYTES + 15) / 16) * 16) + (size_t)grp * N;
     unsigned short *codes = reinterpret_cast<unsigned short *>(smemRaw + ((L::KEY_BYTES + 15) / 16) * 16) + (size_t)grp * N;
 
-    const u32 gidx = blockIdx.x * L::GROUPS + grp;
+    const u32 gidx = blk * L::GROUPS + grp;
     const bool active = gidx < count;
     u32 row = 0, ops = 0, aBeg = 0, aEnd = 0;
     u64 mapOff = 0;
@@ -337,6 +337,37 @@ k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict
 }
 
 template <int G, int E, typename KeyT, typename T, int MODE>
+__global__ void __launch_bounds__(SORT_BLOCK)
+k_sort_rows(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
+            const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
+            const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
+            u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV, const RowDesc *__restrict__ desc,
+            const uint2 *__restrict__ aSeg, unsigned short *__restrict__ rankMap)
+{
+    sort_rows_body<G, E, KeyT, T, MODE>(blockIdx.x, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV, desc, aSeg,
+                                        rankMap);
+}
+
+// The same with a capped grid (LaunchCtx::gridCap): every CTA loops over groups of SORT_BLOCK / G rows.  A separate
+// kernel: the loop costs the one-shot kernel 8 registers per thread.
+template <int G, int E, typename KeyT, typename T, int MODE>
+__global__ void __launch_bounds__(SORT_BLOCK)
+k_sort_rows_loop(const u32 *__restrict__ perm, const u32 count, const u32 *__restrict__ aRp,
+                 const u32 *__restrict__ aCi, const T *__restrict__ aV, const u32 *__restrict__ bRp,
+                 const u32 *__restrict__ bCi, const T *__restrict__ bV, const u32 *__restrict__ rowOps,
+                 u32 *cRp, u32 *__restrict__ cCi, T *__restrict__ cV, const RowDesc *__restrict__ desc,
+                 const uint2 *__restrict__ aSeg, unsigned short *__restrict__ rankMap)
+{
+    constexpr u32 GROUPS = SortLayout<G, E, KeyT, T, MODE>::GROUPS;
+#pragma unroll 1
+    for (u32 blk = blockIdx.x; blk * GROUPS < count; blk += gridDim.x) {
+        sort_rows_body<G, E, KeyT, T, MODE>(blk, perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV, desc, aSeg,
+                                            rankMap);
+        __syncwarp();   // the next row group reuses the lane groups' shared-memory regions
+    }
+}
+
+template <int G, int E, typename KeyT, typename T, int MODE>
 void launch_sort_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32 *aRp, const u32 *aCi,
                       const T *aV, const u32 *bRp, const u32 *bCi, const T *bV, const u32 *rowOps, u32 *cRp,
                       u32 *cCi, T *cV, const RowDesc *desc = nullptr, const uint2 *aSeg = nullptr,
@@ -347,6 +378,17 @@ void launch_sort_rows(const LaunchCtx &lc, const u32 *perm, u32 count, const u32
     if (L::SMEM > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
     const u32 grid = (count + L::GROUPS - 1) / L::GROUPS;
+    if constexpr (MODE == SORT_MAP && G == 32 && E >= 4 && sizeof(KeyT) == 4) {
+        if (lc.gridCap && grid > lc.gridCap) {
+            auto loop = k_sort_rows_loop<G, E, KeyT, T, MODE>;
+            if (L::SMEM > 48 * 1024)
+                cudaFuncSetAttribute(loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+            loop<<<lc.gridCap, SORT_BLOCK, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV,
+                                                                 desc, aSeg, rankMap);
+            ++*lc.launches;
+            return;
+        }
+    }
     kern<<<grid, SORT_BLOCK, L::SMEM, lc.stream>>>(perm, count, aRp, aCi, aV, bRp, bCi, bV, rowOps, cRp, cCi, cV, desc, aSeg,
                                                    rankMap);
     ++*lc.launches;

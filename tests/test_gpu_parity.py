@@ -661,6 +661,68 @@ def test_col_direct_variants(ctx):
         ctx.set_option("col_direct", 0)
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_big_split_variants(ctx, variant):
+    """big_split = 1..3: rows of 4097..16384 products take several CTAs per row, each staging one range of the row's
+    positions (map_split.cuh): class edges, rows that need several batches of A entries, rows that fold into a few
+    columns (the upper ranges stay empty), an R-MAT with hub rows."""
+    rng = np.random.default_rng(77)
+    try:
+        ctx.set_option("big_split", variant)
+        A, B = _rows_with_products([4095, 4096, 4097, 6000, 8191, 8192, 8193, 12345, 16383, 16384, 16385, 700],
+                                   cols=1 << 18, nb=256)
+        got, st = check_case(ctx, A, B, what=f"big_split={variant} class edges")
+        assert st["class_rows"]["sort16384"] == 4 and st["class_rows"]["sort8192"] >= 2
+        # several batches of A entries (more entries than threads), B rows of 0..5 entries
+        nb, cols = 9000, 1 << 19
+        blen = rng.integers(0, 6, nb)
+        br = np.repeat(np.arange(nb), blen)
+        B = M.from_coo(nb, cols, br, rng.integers(0, cols, br.size), seed=78)
+        ar, ac = [], []
+        for i, alen in enumerate([1800, 2500, 3300, 5000, 6400]):
+            ar += [i] * alen
+            ac += list(rng.choice(nb, alen, replace=False))
+        A = M.from_coo(5, nb, ar, ac, seed=79)
+        got, st = check_case(ctx, A, B, what=f"big_split={variant} many short B rows")
+        assert st["class_rows"]["sort16384"] >= 2
+        # heavy folding: ~6000 / ~12000 products per row onto <= 302 columns spread over 2^20
+        nb, cols = 400, 1 << 20
+        pool = np.unique(np.concatenate([[0, cols - 1], rng.integers(0, cols, 300)]))
+        br, bc = [], []
+        for k in range(nb):
+            br += [k] * 40
+            bc += list(rng.choice(pool, 40, replace=False))
+        B = M.from_coo(nb, cols, br, bc, seed=80)
+        ar, ac = [], []
+        for i in range(24):
+            alen = 150 if i % 2 else 300
+            ar += [i] * alen
+            ac += list(rng.choice(nb, alen, replace=False))
+        A = M.from_coo(24, nb, ar, ac, seed=81)
+        got, st = check_case(ctx, A, B, what=f"big_split={variant} folding rows")
+        assert st["class_rows"]["sort16384"] == 12 and st["products"] > 5 * st["nnz_c"]
+        check_case(ctx, M.rmat(15, 16, seed=15), what=f"big_split={variant} rmat15")
+        A32 = M.rmat(14, 16, seed=16, dtype=np.float32)
+        got, _ = gpu_multiply(ctx, A32)
+        A64 = A32.astype(np.float64)
+        assert_csr_equal(got, oracle_multiply(A64, A64), rtol=1e-4, what=f"big_split={variant} fp32")
+    finally:
+        ctx.set_option("big_split", 0)
+
+
+@pytest.mark.parametrize("ctas", [1, 4, 16])
+def test_sym_mix_plan(ctx, ctas):
+    """sym_mix: the 128 / 256 / 512-product sort classes run as capped grids (every CTA loops over row groups) next to
+    the rank kernels instead of after them."""
+    try:
+        ctx.set_option("sym_mix", ctas)
+        for A in (M.rmat(15, 16, seed=15), M.rmat(13, 8, seed=5), M.uniform_random(30000, 30000, 12, seed=6)):
+            got, st = check_case(ctx, A, what=f"sym_mix={ctas}")
+        assert st["class_rows"]["sort256"] > 1000
+    finally:
+        ctx.set_option("sym_mix", 0)
+
+
 @pytest.mark.parametrize("sort_max_value", [16384, 1024, 64])
 def test_tiered_analysis(ctx, sort_max_value):
     """tiered_analysis=1: the analysis gathers only B's row_offsets and fetches column extents in a second pass for
