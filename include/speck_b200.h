@@ -232,6 +232,15 @@ int speck_b200_sharded_destroy(speck_shard_plan *plan);
  *                       matrix: a row costs about as much as 7 products, an entry of A about 1.5 (profiles/r2_notes.md)
  *   "col_direct"        1..3: large mapped numeric shapes stage values only and write column ids straight to C
  *                       (measured slower; default 0)
+ *   "narrow_groups"     2 (default): mapped rows of <= 128 products share a warp (4 / 8 / 16 lanes per row with 2..8
+ *                       products per lane) in the symbolic sort and the numeric kernels; 1: rows of <= 64 products only;
+ *                       0: one row per warp from 17 products
+ *   "big_split"         1..3: rows of 4097..16384 products take several CTAs per row in the numeric phase
+ *                       (measured slower; default 0)
+ *   "flat_min_class"    6 / 7: the 129..256 / 257..512-product classes rank with the flat bitmap kernel instead of the
+ *                       register bitonic sort (measured slower; default 8 = off)
+ *   "sym_mix"           N > 0: the sort kernels of the three largest lane-group classes run as capped grids (about N CTAs
+ *                       per SM) next to the bitmap rank kernels instead of after them (measured slower; default 0)
  *   "seg_num", "hash_count"        experiments kept for the record (profiles/r2_notes.md), off by default
  *   "release_workspace" 1 frees the pooled workspace now. */
 int speck_b200_set_option(speck_ctx *ctx, const char *key, long long value);

@@ -41,6 +41,21 @@ with api.Context(0) as ctx:
     ctx.set_option("flat_sym", 0)
     check(ctx, A, B, what="class boundaries (register-slot symbolic kernel)")
     ctx.set_option("flat_sym", 1)
+    # lane-group shapes (several rows per warp is the default), capped-grid sort kernels, several CTAs per large row
+    S = M.rmat(13, 4, seed=21)
+    for v in (0, 1, 2):
+        ctx.set_option("narrow_groups", v)
+        check(ctx, S, what=f"small rows, narrow_groups={v}")
+    ctx.set_option("sym_mix", 1)
+    check(ctx, M.rmat(13, 16, seed=22), what="sym_mix=1 (k_sort_rows_loop)")
+    ctx.set_option("sym_mix", 0)
+    for v in (1, 2):
+        ctx.set_option("big_split", v)
+        check(ctx, A, B, what=f"class boundaries, big_split={v}")
+    ctx.set_option("big_split", 0)
+    ctx.set_option("flat_min_class", 6)
+    check(ctx, A, B, what="class boundaries, flat_min_class=6")
+    ctx.set_option("flat_min_class", 8)
     F = M.fem3d_like(7, 6, 5)
     for v in (1, 2, 0):
         ctx.set_option("dense_seq", v)

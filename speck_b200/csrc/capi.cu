@@ -99,6 +99,9 @@ struct speck_ctx {
                               // 1 = B segments loaded by the lanes, 2 = staged by TMA bulk copies
     int flatMinClass = NUM_WARP_SORT;   // lane-group classes >= this (6 = 256, 7 = 512 products) rank with the flat bitmap
                               // kernel instead of the register bitonic sort (mapped, two-level matrices only)
+    int narrow = 2;           // lane-group classes of <= 64 (1) / <= 128 (2) products: several rows per warp, 0 = one row
+                              // per warp from 17 products (config-5 matrix: 16.2 -> 15.6 ms, profiles/r2_notes.md)
+    int narrowNum = -1;       // the same for the numeric kernels alone (-1: follow narrow)
     int symMix = 0;           // symbolic phase: > 0 = the lane-group sort kernels of the 128 / 256 / 512-product classes
                               // (instruction-bound) run with about this many CTAs per SM, looping over their rows, next
                               // to the bitmap rank kernels (shared-memory-bound) instead of after them
@@ -381,6 +384,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (!cnt || sortDone[sc]) continue;
         LaunchCtx ls{c->side[sidx++ % c->symStreams], c->smCount, &c->launches};
         const bool mapped = desc && sc >= c->mapMinClass;
+        ls.narrow = mapped ? c->narrow : 0;
         // 64-bit sort keys cost 2-3x (R-MAT scale 24: 28 ps per product in the 512 class): wide matrices rank these
         // rows with the three-level bitmap kernel (u32 throughout) instead
         if (mapped && useRank && rankLevels == 3 && sc >= 6 && sc < NUM_WARP_SORT && sort_keys_wide(sc, colsB))
@@ -473,6 +477,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
         if (!cnt) continue;
         LaunchCtx ls{c->side[sidx++ % numStreams], c->smCount, &c->launches};
         const bool mapped = rankMap && sc < NUM_WARP_SORT && sc >= c->mapMinClass;
+        ls.narrow = mapped ? (c->narrowNum >= 0 ? c->narrowNum : c->narrow) : 0;
         if (mapped && sc >= c->mapCtaMin)   // rows of <= 4 << sc products: 32 / 64 threads x 8 slots
             launch_map_numeric_cta<T>(ls, 4u << sc, desc + binStart[BIN_SORT0 + sc], cnt, aSeg, aV, bCi, bV, rankMap, cCi, cV);
         else if (mapped)
@@ -1233,6 +1238,16 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "flat_min_class")) {
         if (value < 6 || value > NUM_WARP_SORT) return fail(SPECK_ERR_INVALID, "flat_min_class must be in [6, %d]", NUM_WARP_SORT);
         c->flatMinClass = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "narrow_groups")) {
+        if (value < 0 || value > 2) return fail(SPECK_ERR_INVALID, "narrow_groups must be 0, 1 or 2");
+        c->narrow = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "narrow_numeric")) {
+        if (value < -1 || value > 2) return fail(SPECK_ERR_INVALID, "narrow_numeric must be in [-1, 2]");
+        c->narrowNum = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "sym_mix")) {

@@ -95,6 +95,7 @@ struct LaunchCtx {
     cudaStream_t stream;
     int smCount;
     u32 *launches;   // incremented per kernel launch
+    int narrow = 0;  // lane-group classes of <= 64 (1) / <= 128 (2) products: fewer lanes per row, more products per lane
     u32 gridCap = 0; // lane-group sort kernels: at most this many CTAs, each looping over row groups (0: one CTA per group
                      // of rows); lets a long instruction-bound kernel share the SMs with kernels of other streams
 };

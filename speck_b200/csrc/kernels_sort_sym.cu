@@ -23,12 +23,14 @@ void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, bool wideKeys, con
                                                          nullptr, nullptr, desc, aSeg, rankMap);                          \
     } while (0)
     switch (sortClass) {
+        // narrow: several rows per warp (4 / 8 / 16 lanes with 2..8 keys each): the per-row fixed work (descriptor,
+        // scans, searches) is shared by the rows of a warp and more of the network runs inside a lane
         case 0: SB_SYM(4, 1); break;
-        case 1: SB_SYM(8, 1); break;
-        case 2: SB_SYM(16, 1); break;
-        case 3: SB_SYM(32, 1); break;
-        case 4: SB_SYM(32, 2); break;
-        case 5: SB_SYM(32, 4); break;
+        case 1: if (lc.narrow) SB_SYM(4, 2); else SB_SYM(8, 1); break;
+        case 2: if (lc.narrow) SB_SYM(4, 4); else SB_SYM(16, 1); break;
+        case 3: if (lc.narrow) SB_SYM(8, 4); else SB_SYM(32, 1); break;
+        case 4: if (lc.narrow) SB_SYM(16, 4); else SB_SYM(32, 2); break;
+        case 5: if (lc.narrow > 1) SB_SYM(16, 8); else SB_SYM(32, 4); break;
         case 6: SB_SYM(32, 8); break;
         case 7: SB_SYM(32, 16); break;
         default: {

@@ -56,11 +56,11 @@ void launch_map_numeric(const LaunchCtx &lc, int sortClass, const RowDesc *desc,
 #define SB_MAP(G, N) launch_map_rows<G, N, T>(lc, desc, count, aSeg, aV, bCi, bV, rankMap, cCi, cV)
     switch (sortClass) {
         case 0: SB_MAP(4, 4); break;
-        case 1: SB_MAP(8, 8); break;
-        case 2: SB_MAP(16, 16); break;
-        case 3: SB_MAP(32, 32); break;
-        case 4: SB_MAP(32, 64); break;
-        case 5: SB_MAP(32, 128); break;
+        case 1: if (lc.narrow) SB_MAP(4, 8); else SB_MAP(8, 8); break;
+        case 2: if (lc.narrow) SB_MAP(4, 16); else SB_MAP(16, 16); break;
+        case 3: if (lc.narrow) SB_MAP(8, 32); else SB_MAP(32, 32); break;
+        case 4: if (lc.narrow) SB_MAP(16, 64); else SB_MAP(32, 64); break;
+        case 5: if (lc.narrow > 1) SB_MAP(16, 128); else SB_MAP(32, 128); break;
         case 6: SB_MAP(32, 256); break;
         default: SB_MAP(32, 512); break;
     }

@@ -184,7 +184,7 @@ sort_rows_body(const u32 blk, const u32 *__restrict__ perm, const u32 count, con
         const u32 total = __shfl_sync(gmask, incl, G - 1, G);
         const u32 qb = bs - (incl - len);   // position in B of product p of this entry = qb + p
         // U products per lane and iteration (whole-warp groups only): owners first, then all loads, then the stores
-        constexpr int U = (G == 32 && E >= 4) ? 4 : 1;
+        constexpr int U = E >= 4 ? 4 : 1;
         for (u32 p0 = 0; p0 < total; p0 += U * G) {
             u32 q[U], col[U];
             T oAv[U], bv[U];
@@ -461,7 +461,7 @@ k_map_rows(const RowDesc *__restrict__ desc, const u32 count, const uint2 *__res
         const u32 total = __shfl_sync(gmask, incl, G - 1, G);
         const u32 qb = bs - (incl - len);   // position in B of product p of this entry = qb + p
         // U products per lane and iteration (whole-warp groups only): owners first, then all loads, then the stores
-        constexpr int U = (G == 32 && N >= 128) ? 4 : 1;
+        constexpr int U = (N / G >= 4) ? 4 : 1;
         for (u32 p0 = 0; p0 < total; p0 += U * G) {
             u32 q[U], col[U], code[U];
             T oAv[U], bv[U];

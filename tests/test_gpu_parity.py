@@ -723,6 +723,42 @@ def test_sym_mix_plan(ctx, ctas):
         ctx.set_option("sym_mix", 0)
 
 
+@pytest.mark.parametrize("narrow", [0, 1, 2])
+def test_narrow_lane_groups(ctx, narrow):
+    """narrow_groups: rows of <= 64 / <= 128 products share a warp (4 / 8 / 16 lanes per row, 2..8 products per lane) in
+    the sort-symbolic and mapped-numeric lane-group kernels; rows whose A entries exceed the group width take several
+    batches."""
+    try:
+        ctx.set_option("narrow_groups", narrow)
+        targets = list(range(1, 140)) + [255, 256, 257]
+        A, B = _rows_with_products(targets, cols=1 << 16, nb=64)
+        check_case(ctx, A, B, what=f"narrow={narrow} every product count up to 139")
+        # many A entries with tiny B rows: 20..120 entries per row, B rows of 0..2 entries
+        rng = np.random.default_rng(91)
+        nb, cols = 5000, 1 << 18
+        blen = rng.integers(0, 3, nb)
+        br = np.repeat(np.arange(nb), blen)
+        B = M.from_coo(nb, cols, br, rng.integers(0, cols, br.size), seed=92)
+        ar, ac = [], []
+        for i in range(400):
+            alen = int(rng.integers(20, 121))
+            ar += [i] * alen
+            ac += list(rng.choice(nb, alen, replace=False))
+        A = M.from_coo(400, nb, ar, ac, seed=93)
+        check_case(ctx, A, B, what=f"narrow={narrow} many short B rows")
+        # folding inside small rows
+        A = M.uniform_random(3000, 300, 6, seed=94)
+        B = M.uniform_random(300, 40, 5, seed=95)
+        got, st = check_case(ctx, A, B, what=f"narrow={narrow} folding")
+        check_case(ctx, M.rmat(14, 4, seed=17), what=f"narrow={narrow} rmat14 ef4")
+        A32 = M.rmat(13, 4, seed=18, dtype=np.float32)
+        got, _ = gpu_multiply(ctx, A32)
+        A64 = A32.astype(np.float64)
+        assert_csr_equal(got, oracle_multiply(A64, A64), rtol=1e-4, what=f"narrow={narrow} fp32")
+    finally:
+        ctx.set_option("narrow_groups", 2)
+
+
 @pytest.mark.parametrize("sort_max_value", [16384, 1024, 64])
 def test_tiered_analysis(ctx, sort_max_value):
     """tiered_analysis=1: the analysis gathers only B's row_offsets and fetches column extents in a second pass for
