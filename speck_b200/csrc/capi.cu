@@ -1241,12 +1241,12 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
         return SPECK_OK;
     }
     if (!strcmp(key, "narrow_groups")) {
-        if (value < 0 || value > 2) return fail(SPECK_ERR_INVALID, "narrow_groups must be 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(SPECK_ERR_INVALID, "narrow_groups must be in [0, 3]");
         c->narrow = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "narrow_numeric")) {
-        if (value < -1 || value > 2) return fail(SPECK_ERR_INVALID, "narrow_numeric must be in [-1, 2]");
+        if (value < -1 || value > 3) return fail(SPECK_ERR_INVALID, "narrow_numeric must be in [-1, 3]");
         c->narrowNum = (int)value;
         return SPECK_OK;
     }

@@ -31,7 +31,7 @@ void launch_sort_symbolic(const LaunchCtx &lc, int sortClass, bool wideKeys, con
         case 3: if (lc.narrow) SB_SYM(8, 4); else SB_SYM(32, 1); break;
         case 4: if (lc.narrow) SB_SYM(16, 4); else SB_SYM(32, 2); break;
         case 5: if (lc.narrow > 1) SB_SYM(16, 8); else SB_SYM(32, 4); break;
-        case 6: SB_SYM(32, 8); break;
+        case 6: if (lc.narrow > 2) SB_SYM(16, 16); else SB_SYM(32, 8); break;
         case 7: SB_SYM(32, 16); break;
         default: {
             const int warps = cta_class_warps(sortClass - NUM_WARP_SORT);

@@ -61,7 +61,7 @@ void launch_map_numeric(const LaunchCtx &lc, int sortClass, const RowDesc *desc,
         case 3: if (lc.narrow) SB_MAP(8, 32); else SB_MAP(32, 32); break;
         case 4: if (lc.narrow) SB_MAP(16, 64); else SB_MAP(32, 64); break;
         case 5: if (lc.narrow > 1) SB_MAP(16, 128); else SB_MAP(32, 128); break;
-        case 6: SB_MAP(32, 256); break;
+        case 6: if (lc.narrow > 2) SB_MAP(16, 256); else SB_MAP(32, 256); break;
         default: SB_MAP(32, 512); break;
     }
 #undef SB_MAP

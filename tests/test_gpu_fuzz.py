@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 OPTIONS = {"sort_max": [16384, 8192, 1024, 64], "rank_path": [0, 1], "rank_map": [0, 1], "flat_sym": [0, 1],
            "flat_e": [8, 16], "seg_num": [0, 1], "dense_seq": [0, 1, 2], "test_set": [0, 1], "spin_wait": [0, 1],
            "tiered_analysis": [0, 1], "col_direct": [0, 0, 1, 2, 3], "big_split": [0, 1, 2, 3], "sym_mix": [0, 0, 1, 3],
-           "flat_min_class": [8, 8, 7, 6], "narrow_groups": [0, 1, 2],
+           "flat_min_class": [8, 8, 7, 6], "narrow_groups": [0, 1, 2, 3],
            "deterministic": [0, 0, 0, 1]}
 DEFAULTS = {"sort_max": 16384, "rank_path": 1, "rank_map": 1, "flat_sym": 1, "flat_e": 8, "seg_num": 0, "dense_seq": 1,
             "test_set": 1, "spin_wait": 1, "tiered_analysis": 0, "col_direct": 0, "big_split": 0, "sym_mix": 0, "flat_min_class": 8, "narrow_groups": 2,

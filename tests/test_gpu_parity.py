@@ -723,7 +723,7 @@ def test_sym_mix_plan(ctx, ctas):
         ctx.set_option("sym_mix", 0)
 
 
-@pytest.mark.parametrize("narrow", [0, 1, 2])
+@pytest.mark.parametrize("narrow", [0, 1, 2, 3])
 def test_narrow_lane_groups(ctx, narrow):
     """narrow_groups: rows of <= 64 / <= 128 products share a warp (4 / 8 / 16 lanes per row, 2..8 products per lane) in
     the sort-symbolic and mapped-numeric lane-group kernels; rows whose A entries exceed the group width take several
