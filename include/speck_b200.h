@@ -234,7 +234,8 @@ int speck_b200_sharded_destroy(speck_shard_plan *plan);
  *                       (measured slower; default 0)
  *   "narrow_groups"     2 (default): mapped rows of <= 128 products share a warp (4 / 8 / 16 lanes per row with 2..8
  *                       products per lane) in the symbolic sort and the numeric kernels; 1: rows of <= 64 products only;
- *                       0: one row per warp from 17 products
+ *                       0: one row per warp from 17 products; 3: the 256-product class as well (measured slower);
+ *                       "narrow_numeric" -1 (default: follow narrow_groups) .. 3 sets the numeric kernels alone
  *   "big_split"         1..3: rows of 4097..16384 products take several CTAs per row in the numeric phase
  *                       (measured slower; default 0)
  *   "flat_min_class"    6 / 7: the 129..256 / 257..512-product classes rank with the flat bitmap kernel instead of the

@@ -61,8 +61,9 @@ struct speck_ctx {
     int smCount = 0;
     cudaStream_t main = nullptr;
     cudaStream_t side[NSTREAMS] = {};
-    cudaEvent_t evFork = nullptr, evJoin[NSTREAMS] = {};
-    cudaEvent_t evStage[6] = {};
+    cudaEvent_t evFork = nullptr, evCopy = nullptr, evJoin[NSTREAMS] = {};
+    cudaEvent_t evStage[8] = {};   // 0..5 stage boundaries, 6..7 around the descriptor update that runs during the second read-back
+    bool descTimed = false;
     Scalars *dSc = nullptr;
     Scalars *hSc = nullptr;  // pinned, mapped: written by k_publish (or by a plain D2H copy when spinWait is off)
     volatile u32 *hSeq = nullptr;   // sequence word next to the mirror, polled by the host
@@ -117,6 +118,8 @@ struct speck_ctx {
     bool rankMapOn = true;    // symbolic phase records every product's sorted position (2 B per product)
     u32 launches = 0;
     speck_stats stats = {};
+    bool stageTimesPending = false;   // the stage times of `stats` are still in the events (read on demand: five
+                                      // cudaEventElapsedTime calls cost ~8 us, a third of the host overhead of a multiply)
 };
 
 namespace {
@@ -158,15 +161,25 @@ bool sort_keys_wide(int sc, u32 colsB)
 // Scalars to the host in the middle of a multiply.  Polling a word in mapped pinned memory costs 2-3 us against
 // ~15-20 us for cudaMemcpyAsync + cudaStreamSynchronize; the stream is queried now and then so that a failed
 // kernel cannot hang the host.
-int read_scalars(speck_ctx *c, LaunchCtx &lc)
+// publish_scalars starts the read-back, wait_scalars completes it: kernels launched in between run on the device
+// while the scalars travel to the host
+void publish_scalars(speck_ctx *c, LaunchCtx &lc)
 {
     if (!c->spinWait) {
-        CU_TRY(cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main));
-        CU_TRY(cudaStreamSynchronize(c->main));
+        cudaMemcpyAsync(c->hSc, c->dSc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->main);
+        cudaEventRecord(c->evCopy, c->main);
+        return;
+    }
+    launch_publish(lc, c->dSc, c->hSc, c->hSeq, ++c->seq);
+}
+
+int wait_scalars(speck_ctx *c)
+{
+    if (!c->spinWait) {
+        CU_TRY(cudaEventSynchronize(c->evCopy));
         return SPECK_OK;
     }
-    const u32 seq = ++c->seq;
-    launch_publish(lc, c->dSc, c->hSc, c->hSeq, seq);
+    const u32 seq = c->seq;
     for (u64 spins = 0;; ++spins) {
         if (*c->hSeq == seq) break;
         if ((spins & 0x3fff) == 0x3fff) {
@@ -180,6 +193,12 @@ int read_scalars(speck_ctx *c, LaunchCtx &lc)
         }
     }
     return SPECK_OK;
+}
+
+int read_scalars(speck_ctx *c, LaunchCtx &lc)
+{
+    publish_scalars(c, lc);
+    return wait_scalars(c);
 }
 
 void fork_streams(speck_ctx *c, int n = NSIDE)
@@ -196,10 +215,29 @@ void join_streams(speck_ctx *c, int n = NSIDE)
     }
 }
 
+// stage times of the last multiply, from its events (they stay valid until the next multiply records them again)
+void finish_stage_times(speck_ctx *c)
+{
+    if (!c->stageTimesPending) return;
+    c->stageTimesPending = false;
+    speck_stats &st = c->stats;
+    cudaEventElapsedTime(&st.ms_analysis, c->evStage[0], c->evStage[1]);
+    cudaEventElapsedTime(&st.ms_symbolic, c->evStage[1], c->evStage[2]);
+    cudaEventElapsedTime(&st.ms_scan, c->evStage[2], c->evStage[3]);
+    cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
+    if (c->descTimed) {
+        float d = 0.f;
+        cudaEventElapsedTime(&d, c->evStage[6], c->evStage[7]);
+        st.ms_numeric += d;
+    }
+    cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
+}
+
 template <typename T>
 int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr *C, speck_timings *tm)
 {
     if (!c || !A || !B || !C) return fail(SPECK_ERR_INVALID, "null argument");
+    c->stageTimesPending = false;   // the events are about to be recorded again
     // guards of the reference, source/GPU/Multiply.cu:57-70
     if (B->cols > (1u << 27)) return fail(SPECK_ERR_TOO_LARGE, "matrix B has more than %d columns (%zu)", 1 << 27, B->cols);
     if (A->rows > (1u << 27)) return fail(SPECK_ERR_TOO_LARGE, "matrix A has more than %d rows (%zu)", 1 << 27, A->rows);
@@ -404,7 +442,15 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // ---- scan + nnz read-back
     launch_scan(lc, cRp, rows + 1, (u64 *)c->tileState.p, c->dSc);
     cudaEventRecord(c->evStage[3], c->main);
-    if ((rc = read_scalars(c, lc))) return rc;
+    publish_scalars(c, lc);
+    // the descriptors take their C offsets while nnz(C) travels to the host (timed with the numeric phase)
+    c->descTimed = rankMap != nullptr;
+    if (rankMap) {
+        cudaEventRecord(c->evStage[6], c->main);
+        launch_desc_numeric(lc, binStart[NUM_BINS], cRp, desc);
+        cudaEventRecord(c->evStage[7], c->main);
+    }
+    if ((rc = wait_scalars(c))) return rc;
     CU_TRY(cudaGetLastError());
     const u64 nnzC = c->hSc->nnzC;
     const int seqKind = c->denseSeq ? c->denseSeq : (det ? 1 : 0);
@@ -434,7 +480,6 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     // ---- numeric
     const int numStreams = c->numStreams ? c->numStreams : (s1.products >= (1ull << 27) ? 1 : NSIDE);
     cudaEventRecord(c->evStage[4], c->main);
-    if (rankMap) launch_desc_numeric(lc, binStart[NUM_BINS], cRp, desc);
     fork_streams(c);
     sidx = 0;
     for (int loc = 0; loc < 2; ++loc) {
@@ -504,14 +549,11 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
     st.max_row_products = s1.maxRowProducts;
     for (int b = 0; b < NUM_BINS; ++b) st.class_rows[b] = s1.binCount[b];
     st.kernel_launches = c->launches;
-    cudaEventElapsedTime(&st.ms_analysis, c->evStage[0], c->evStage[1]);
-    cudaEventElapsedTime(&st.ms_symbolic, c->evStage[1], c->evStage[2]);
-    cudaEventElapsedTime(&st.ms_scan, c->evStage[2], c->evStage[3]);
-    cudaEventElapsedTime(&st.ms_numeric, c->evStage[4], c->evStage[5]);
-    cudaEventElapsedTime(&st.ms_total, c->evStage[0], c->evStage[5]);
+    c->stageTimesPending = true;   // read by speck_b200_get_stats / the sharded summary / below when timings are asked for
     st.workspace_bytes = c->rowOps.cap + c->perm.cap + c->rowMin.cap + c->rowMax.cap + c->tileState.cap + c->bitmapStore.cap +
                          c->mapLen.cap + c->mapBase.cap + c->rankMap.cap + c->aSeg.cap + c->aOff.cap + c->desc.cap + c->rowInfo.cap;
     if (tm) {
+        finish_stage_times(c);
         float allocMs = 0.f;
         cudaEventElapsedTime(&allocMs, c->evStage[3], c->evStage[4]);
         tm->init = 0.f;
@@ -699,6 +741,7 @@ int speck_b200_create(int device, speck_ctx **out)
             CU_TRY(cudaEventCreateWithFlags(&c->evJoin[i], cudaEventDisableTiming));
         }
         CU_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->evCopy, cudaEventDisableTiming));
         for (auto &e : c->evStage) CU_TRY(cudaEventCreate(&e));
         CU_TRY(cudaMalloc(&c->dSc, sizeof(Scalars)));
         CU_TRY(cudaHostAlloc(&c->hSc, sizeof(Scalars) + 64, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -736,6 +779,7 @@ int speck_b200_destroy(speck_ctx *c)
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
     }
     if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evCopy) cudaEventDestroy(c->evCopy);
     if (c->main) cudaStreamDestroy(c->main);
     delete c;
     return SPECK_OK;
@@ -763,6 +807,8 @@ int speck_b200_spgemm_host_f32(speck_ctx *c, const speck_csr *A, const speck_csr
 int speck_b200_get_stats(const speck_ctx *c, speck_stats *out)
 {
     if (!c || !out) return fail(SPECK_ERR_INVALID, "null argument");
+    cudaSetDevice(c->device);
+    finish_stage_times(const_cast<speck_ctx *>(c));   // the stage times are read from the events on first use
     *out = c->stats;
     return SPECK_OK;
 }
@@ -1074,6 +1120,8 @@ int speck_b200_sharded_multiply(speck_shard_plan *p, speck_shard_info *info)
         info->shards = p->n;
         for (int g = 0; g <= p->n; ++g) info->cuts[g] = p->cuts[g];
         for (int g = 0; g < p->n; ++g) {
+            cudaSetDevice(p->ctx[g]->device);
+            finish_stage_times(p->ctx[g]);
             info->products[g] = p->ctx[g]->stats.products;
             info->nnz_c[g] = p->dC[g].nnz;
             info->ms_device[g] = p->ctx[g]->stats.ms_total;
