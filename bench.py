@@ -310,6 +310,9 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference spECK CUDA build (oracle/_ref) on the same GPU")
     ap.add_argument("--no-sweep", action="store_true", help="N = 1: skip the sweep over the other BASELINE configs")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling figure")
+    ap.add_argument("--concat", default="push", choices=["push", "nccl", "both"],
+                    help="N > 1: how the slabs of C reach GPU 0 for the extra concatenation figure: own push kernel over "
+                         "IPC-opened peer memory (falls back to NCCL when IPC is unavailable), NCCL send/recv, or both")
     ap.add_argument("--part-row-cost", type=int, default=8, help="N > 1: cost of a row in products for the partition")
     ap.add_argument("--part-entry-cost", type=int, default=2, help="N > 1: cost of an entry of A in products for the partition")
     ap.add_argument("--sort-max", type=int, default=0)
@@ -335,6 +338,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the only NCCL traffic of this bench is point-to-point (slabs of C -> GPU 0, outside the multiply): with its
+        # default of a few channels per peer one send/recv pair moves ~200 GB/s of NVLink's 900
+        os.environ.setdefault("NCCL_NCHANNELS_PER_PEER", "32")
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = api.Context(local_rank)
@@ -452,59 +460,142 @@ def main():
                     self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
             def dview(ptr, n, typestr, dtype):
+                ptr = getattr(ptr, "value", ptr)
                 return torch.as_tensor(_Arr(ptr, n, typestr), device=dev) if (ptr and n) else torch.zeros(n, dtype=dtype, device=dev)
             c_rp = dview(dC.s.row_offsets if nnzC else None, slab.rows + 1, "<i4", torch.int32)
             c_ci = dview(dC.s.col_ids, nnzC, "<i4", torch.int32)
             c_v = dview(dC.s.data, nnzC, "<f8", torch.float64)
-            if rank == 0:
-                g_rp = torch.empty(A.rows + 1, dtype=torch.int32, device=dev)
-                g_ci = torch.empty(total, dtype=torch.int32, device=dev)
-                g_v = torch.empty(total, dtype=torch.float64, device=dev)
-            # NCCL point-to-point connections are set up lazily on first use: warm them up outside the timed region
-            warm = torch.zeros(4, dtype=torch.int32, device=dev)
-            ops = ([dist.P2POp(dist.irecv, torch.zeros(4, dtype=torch.int32, device=dev), r) for r in range(1, world)]
-                   if rank == 0 else [dist.P2POp(dist.isend, warm, 0)])
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if rank == 0:
-                # every slab lands at its final position (one grouped NCCL receive), row_offsets get the slab's base added
-                tmp_rp, ops, base, bases = {}, [], 0, []
-                for r in range(world):
-                    r0, r1 = int(cuts[r]), int(cuts[r + 1])
-                    bases.append(base)
-                    if r > 0:
-                        tmp_rp[r] = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=dev)
-                        ops.append(dist.P2POp(dist.irecv, tmp_rp[r], r))
-                        if cnt[r]:
-                            ops.append(dist.P2POp(dist.irecv, g_ci[base:base + cnt[r]], r))
-                            ops.append(dist.P2POp(dist.irecv, g_v[base:base + cnt[r]], r))
-                    base += cnt[r]
-                works = dist.batch_isend_irecv(ops) if ops else []
-                g_ci[:cnt[0]] = c_ci
-                g_v[:cnt[0]] = c_v
-                g_rp[int(cuts[0]):int(cuts[1]) + 1] = c_rp
-                for w in works:
-                    w.wait()
-                for r in range(1, world):     # offset fix-up (values below 2^32 wrap correctly in int32)
-                    g_rp[int(cuts[r]):int(cuts[r + 1]) + 1] = tmp_rp[r] + bases[r]
-            else:
-                ops = [dist.P2POp(dist.isend, c_rp, 0)]
-                if nnzC:
-                    ops += [dist.P2POp(dist.isend, c_ci, 0), dist.P2POp(dist.isend, c_v, 0)]
+            # checksums of the slabs, to verify the concatenated arrays on rank 0
+            chk = torch.stack([c_ci.sum(dtype=torch.int64).to(torch.float64), c_v.sum(dtype=torch.float64)])
+            dist.all_reduce(chk)
+
+            def concat_push():
+                """Own kernel over peer memory: rank 0 exports the arrays of the concatenated C through CUDA IPC, every
+                rank pushes its slab into them (16-byte peer stores over NVLink, row_offsets fix-up fused)."""
+                ptrs, mine, ok = None, rank == 0, 1
+                try:
+                    if rank == 0:
+                        ptrs = [ctx._alloc((A.rows + 1) * 4), ctx._alloc(max(total, 1) * 4), ctx._alloc(max(total, 1) * 8)]
+                        hb = b"".join(ctx.ipc_export(p) for p in ptrs)
+                        ht = torch.tensor(list(hb), dtype=torch.uint8, device=dev)
+                    else:
+                        ht = torch.empty(3 * ctx.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+                except Exception as e:   # keep the collectives below matched on every rank
+                    ok, ht = 0, torch.zeros(3 * ctx.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+                    sys.stderr.write(f"[bench] rank {rank}: IPC export failed: {e}\n")
+                dist.broadcast(ht, 0)
+                if rank != 0 and ok:
+                    try:
+                        hb = bytes(ht.cpu().numpy().tobytes())
+                        n = ctx.IPC_HANDLE_BYTES
+                        ptrs = [ctx.ipc_open(hb[i * n:(i + 1) * n]) for i in range(3)]
+                    except Exception as e:
+                        ok = 0
+                        sys.stderr.write(f"[bench] rank {rank}: IPC open failed: {e}\n")
+                flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                res = None
+                if int(flag.item()):
+                    base, last = sum(cnt[:rank]), rank == world - 1
+                    ms, bad = 0.0, 0
+                    try:
+                        ctx.push_slab(dC, base, int(cuts[rank]), last, *ptrs)      # untimed: first touch of the peer mapping
+                    except Exception as e:   # every rank still reaches the barriers below
+                        bad = 1
+                        sys.stderr.write(f"[bench] rank {rank}: push failed: {e}\n")
+                    barrier()
+                    try:
+                        if not bad:
+                            ms = ctx.push_slab(dC, base, int(cuts[rank]), last, *ptrs)  # CUDA-event time of this rank's kernel
+                    except Exception as e:
+                        bad = 1
+                        sys.stderr.write(f"[bench] rank {rank}: push failed: {e}\n")
+                    barrier()
+                    t = torch.tensor([ms, float(bad)], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    if t[1].item() == 0:
+                        res = {"ms": float(t[0].item()), "method": "own push kernel: 16-byte peer stores over NVLink into "
+                               "IPC-opened arrays on GPU 0, row_offsets fix-up fused (speck_b200_push_slab_f64)"}
+                    if res is not None and rank == 0:
+                        g_rp = dview(ptrs[0], A.rows + 1, "<i4", torch.int32)
+                        g_ci = dview(ptrs[1], total, "<i4", torch.int32)
+                        g_v = dview(ptrs[2], total, "<f8", torch.float64)
+                        got = torch.stack([g_ci.sum(dtype=torch.int64).to(torch.float64), g_v.sum(dtype=torch.float64)])
+                        res["row_offsets_last_equals_total"] = bool((int(g_rp[-1].item()) & 0xffffffff) == total)
+                        res["row_offsets_monotone"] = bool((g_rp.to(torch.int64) & 0xffffffff).diff().ge(0).all().item())
+                        res["checksums_match_slabs"] = bool(got[0].item() == chk[0].item()
+                                                            and abs(got[1].item() - chk[1].item()) <= 1e-9 * abs(chk[1].item()))
+                        del g_rp, g_ci, g_v
+                    torch.cuda.synchronize()
+                if rank != 0 and ptrs:
+                    for p_ in ptrs:
+                        ctx.ipc_close(p_)
+                barrier()
+                if rank == 0 and ptrs:
+                    for p_ in ptrs:
+                        ctx.lib.speck_b200_free(ctx.h, p_)
+                return res
+
+            def concat_nccl():
+                if rank == 0:
+                    g_rp = torch.empty(A.rows + 1, dtype=torch.int32, device=dev)
+                    g_ci = torch.empty(total, dtype=torch.int32, device=dev)
+                    g_v = torch.empty(total, dtype=torch.float64, device=dev)
+                # NCCL point-to-point connections are set up lazily on first use: warm them up outside the timed region
+                warm = torch.zeros(4, dtype=torch.int32, device=dev)
+                ops = ([dist.P2POp(dist.irecv, torch.zeros(4, dtype=torch.int32, device=dev), r) for r in range(1, world)]
+                       if rank == 0 else [dist.P2POp(dist.isend, warm, 0)])
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
-            e1.record()
-            barrier()
-            concat_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(concat_ms, op=dist.ReduceOp.MAX)
-            concat["ms"] = float(concat_ms.item())
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if rank == 0:
+                    # every slab lands at its final position (one grouped NCCL receive), row_offsets get the slab's base added
+                    tmp_rp, ops, base, bases = {}, [], 0, []
+                    for r in range(world):
+                        r0, r1 = int(cuts[r]), int(cuts[r + 1])
+                        bases.append(base)
+                        if r > 0:
+                            tmp_rp[r] = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=dev)
+                            ops.append(dist.P2POp(dist.irecv, tmp_rp[r], r))
+                            if cnt[r]:
+                                ops.append(dist.P2POp(dist.irecv, g_ci[base:base + cnt[r]], r))
+                                ops.append(dist.P2POp(dist.irecv, g_v[base:base + cnt[r]], r))
+                        base += cnt[r]
+                    works = dist.batch_isend_irecv(ops) if ops else []
+                    g_ci[:cnt[0]] = c_ci
+                    g_v[:cnt[0]] = c_v
+                    g_rp[int(cuts[0]):int(cuts[1]) + 1] = c_rp
+                    for w in works:
+                        w.wait()
+                    for r in range(1, world):     # offset fix-up (values below 2^32 wrap correctly in int32)
+                        g_rp[int(cuts[r]):int(cuts[r + 1]) + 1] = tmp_rp[r] + bases[r]
+                else:
+                    ops = [dist.P2POp(dist.isend, c_rp, 0)]
+                    if nnzC:
+                        ops += [dist.P2POp(dist.isend, c_ci, 0), dist.P2POp(dist.isend, c_v, 0)]
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                e1.record()
+                barrier()
+                concat_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                dist.all_reduce(concat_ms, op=dist.ReduceOp.MAX)
+                res = {"ms": float(concat_ms.item()), "method": "NCCL grouped send / recv + offset add"}
+                if rank == 0:
+                    res["row_offsets_last_equals_total"] = bool((int(g_rp[-1].item()) & 0xffffffff) == total)
+                    del g_rp, g_ci, g_v
+                return res
+
+            res = concat_push() if args.concat in ("push", "both") else None
+            if res is None or args.concat == "both":
+                r2 = concat_nccl()
+                if res is None:
+                    res = r2
+                else:
+                    res["nccl_send_recv_ms"] = r2["ms"]
+            concat.update(res)
             concat["bytes_moved"] = int(12 * (total - cnt[0]) + 4 * (A.rows + world))
-            if rank == 0:
-                concat["row_offsets_last_equals_total"] = bool((int(g_rp[-1].item()) & 0xffffffff) == total)
-                del g_rp, g_ci, g_v
         else:
             concat["skipped"] = "total nnz(C) >= 2^32: C stays distributed (u32 row_offsets of the spECK API)"
         extra["concat_on_gpu0"] = concat

@@ -203,6 +203,22 @@ int speck_b200_sharded_concat(speck_shard_plan *plan, speck_csr *C, speck_shard_
 int speck_b200_sharded_slab(speck_shard_plan *plan, int g, speck_csr *A_slab, speck_csr *C_slab);
 int speck_b200_sharded_destroy(speck_shard_plan *plan);
 
+/* One process per GPU (torchrun / MPI launches; bench.py --gpus N): concatenation of the slabs of C on one device WITHOUT
+ * a collective library.  The gathering process allocates the three arrays of the concatenated C (speck_b200_malloc) and
+ * exports them (CUDA IPC, 64-byte handles that travel over any host channel); every other process opens them and PUSHES
+ * its slab with one kernel of 16-byte peer stores over NVLink / NVSwitch: col_ids and values at the slab's nnz offset,
+ * row_offsets with that offset added (the fix-up is fused into the transfer).  The gathering process pushes its own
+ * slab the same way (local stores).  `last` != 0: the slab also writes the final row_offsets[rows] entry.
+ * device_ms (may be NULL): CUDA-event time of the push kernel.  The call returns when the stores are complete. */
+#define SPECK_IPC_HANDLE_BYTES 64
+int speck_b200_ipc_export(speck_ctx *ctx, const void *dptr, unsigned char handle[SPECK_IPC_HANDLE_BYTES]);
+int speck_b200_ipc_open(speck_ctx *ctx, const unsigned char handle[SPECK_IPC_HANDLE_BYTES], void **dptr);
+int speck_b200_ipc_close(speck_ctx *ctx, void *dptr);
+int speck_b200_push_slab_f64(speck_ctx *ctx, const speck_csr *C_slab, uint64_t nnz_base, uint32_t row_base, int last,
+                             uint32_t *dst_row_offsets, uint32_t *dst_col_ids, double *dst_data, float *device_ms);
+int speck_b200_push_slab_f32(speck_ctx *ctx, const speck_csr *C_slab, uint64_t nnz_base, uint32_t row_base, int last,
+                             uint32_t *dst_row_offsets, uint32_t *dst_col_ids, float *dst_data, float *device_ms);
+
 /* Tuning knobs (integers; the defaults are the measured best, the switches exist so that the
  * tests can drive every kernel family over the same inputs):
  *   "sort_max"          largest row-product count handled by the sort / rank classes (power of two or

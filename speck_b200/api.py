@@ -79,7 +79,8 @@ EXPORTS = [
     "speck_b200_compare_report_f64", "speck_b200_compare_report_f32", "speck_b200_partition_rows",
     "speck_b200_coo_to_csr_f64", "speck_b200_coo_to_csr_f32", "speck_b200_sharded_create_f64", "speck_b200_sharded_create_f32",
     "speck_b200_sharded_multiply", "speck_b200_sharded_concat", "speck_b200_sharded_slab",
-    "speck_b200_sharded_destroy",
+    "speck_b200_sharded_destroy", "speck_b200_ipc_export", "speck_b200_ipc_open", "speck_b200_ipc_close",
+    "speck_b200_push_slab_f64", "speck_b200_push_slab_f32",
 ]
 
 _lib = None
@@ -131,6 +132,12 @@ def load_library():
     lib.speck_b200_sharded_concat.argtypes = [vp, P(CsrStruct), P(ShardInfoStruct)]
     lib.speck_b200_sharded_slab.argtypes = [vp, ctypes.c_int, P(CsrStruct), P(CsrStruct)]
     lib.speck_b200_sharded_destroy.argtypes = [vp]
+    lib.speck_b200_ipc_export.argtypes = [vp, vp, ctypes.c_char_p]
+    lib.speck_b200_ipc_open.argtypes = [vp, ctypes.c_char_p, P(vp)]
+    lib.speck_b200_ipc_close.argtypes = [vp, vp]
+    for n in ("speck_b200_push_slab_f64", "speck_b200_push_slab_f32"):
+        getattr(lib, n).argtypes = [vp, P(CsrStruct), ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, vp, vp, vp,
+                                    P(ctypes.c_float)]
     _lib = lib
     return lib
 
@@ -203,6 +210,31 @@ class Context:
         p = ctypes.c_void_p()
         _check(self.lib.speck_b200_malloc(self.h, ctypes.byref(p), nbytes))
         return p
+
+    # ---- one process per GPU: the concatenated C lives on one device, the others push their slabs into it
+    IPC_HANDLE_BYTES = 64
+
+    def ipc_export(self, dptr) -> bytes:
+        """64-byte CUDA IPC handle of a device allocation made by this library (speck_b200_malloc)."""
+        buf = ctypes.create_string_buffer(self.IPC_HANDLE_BYTES)
+        _check(self.lib.speck_b200_ipc_export(self.h, dptr, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes):
+        p = ctypes.c_void_p()
+        _check(self.lib.speck_b200_ipc_open(self.h, ctypes.create_string_buffer(handle, self.IPC_HANDLE_BYTES), ctypes.byref(p)))
+        return p
+
+    def ipc_close(self, dptr):
+        _check(self.lib.speck_b200_ipc_close(self.h, dptr))
+
+    def push_slab(self, slab: DeviceCSR, nnz_base, row_base, last, dst_row_offsets, dst_col_ids, dst_data):
+        """Slab of C -> its place in the concatenated C (local or IPC-opened peer arrays); returns the device ms."""
+        fn = self.lib.speck_b200_push_slab_f32 if slab.dtype == np.float32 else self.lib.speck_b200_push_slab_f64
+        ms = ctypes.c_float(0)
+        _check(fn(self.h, ctypes.byref(slab.s), int(nnz_base), int(row_base), int(bool(last)), dst_row_offsets, dst_col_ids,
+                  dst_data, ctypes.byref(ms)))
+        return float(ms.value)
 
     def upload(self, m: HostCSR) -> DeviceCSR:
         d = DeviceCSR(self, m.data.dtype)

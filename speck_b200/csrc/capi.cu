@@ -705,6 +705,36 @@ int compare_impl(speck_ctx *c, const speck_csr *ref, const speck_csr *cmp, int c
 
 }  // namespace
 
+template <typename T>
+int push_slab_impl(speck_ctx *c, const speck_csr *S, uint64_t nnzBase, uint32_t rowBase, int last, uint32_t *dstRp,
+                   uint32_t *dstCi, T *dstV, float *deviceMs)
+{
+    if (!c || !S || !dstRp) return fail(SPECK_ERR_INVALID, "null argument");
+    if (deviceMs) *deviceMs = 0.f;
+    if (S->nnz && (!S->col_ids || !S->data || !S->row_offsets || !dstCi || !dstV)) return fail(SPECK_ERR_INVALID, "null CSR array");
+    if (nnzBase + S->nnz > 0xffffffffull)
+        return fail(SPECK_ERR_OVERFLOW, "concatenated nnz(C) does not fit the u32 row_offsets of the spECK API: keep C distributed");
+    CU_TRY(cudaSetDevice(c->device));
+    const u32 rowsOut = (u32)S->rows + (last ? 1u : 0u);
+    u32 launches = 0;
+    LaunchCtx lc{c->main, c->smCount, &launches};
+    cudaEventRecord(c->evStage[6], c->main);
+    if (S->nnz && S->row_offsets) {
+        launch_push_slab<T>(lc, S->row_offsets, S->col_ids, (const T *)S->data, rowsOut, S->nnz, nnzBase, rowBase, dstRp,
+                            dstCi, dstV);
+    } else if (rowsOut) {   // empty slab (the device conventions leave its row_offsets stale or null): every row starts at nnzBase
+        std::vector<u32> fill((size_t)rowsOut, (u32)nnzBase);
+        CU_TRY(cudaMemcpyAsync(dstRp + rowBase, fill.data(), fill.size() * 4, cudaMemcpyHostToDevice, c->main));
+        CU_TRY(cudaStreamSynchronize(c->main));
+    }
+    cudaEventRecord(c->evStage[7], c->main);
+    CU_TRY(cudaStreamSynchronize(c->main));
+    CU_TRY(cudaGetLastError());
+    if (deviceMs) cudaEventElapsedTime(deviceMs, c->evStage[6], c->evStage[7]);
+    c->descTimed = false;   // the two events were borrowed from the stage timers
+    return SPECK_OK;
+}
+
 extern "C" {
 
 int speck_b200_abi_version(void) { return SPECK_B200_ABI_VERSION; }
@@ -1197,6 +1227,50 @@ int speck_b200_sharded_concat(speck_shard_plan *p, speck_csr *C, speck_shard_inf
         info->ms_concat = (float)(now_ms() - t0);
     }
     return SPECK_OK;
+}
+
+// ---- one process per GPU: CUDA IPC handles of the concatenated C and the push of a slab into it
+int speck_b200_ipc_export(speck_ctx *c, const void *dptr, unsigned char handle[SPECK_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPECK_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    if (!c || !dptr || !handle) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    memcpy(handle, &h, sizeof(h));
+    return SPECK_OK;
+}
+
+int speck_b200_ipc_open(speck_ctx *c, const unsigned char handle[SPECK_IPC_HANDLE_BYTES], void **dptr)
+{
+    if (!c || !dptr || !handle) return fail(SPECK_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    *dptr = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));   // maps the peer allocation, enables peer access
+    return SPECK_OK;
+}
+
+int speck_b200_ipc_close(speck_ctx *c, void *dptr)
+{
+    if (!c) return fail(SPECK_ERR_INVALID, "null argument");
+    if (!dptr) return SPECK_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaIpcCloseMemHandle(dptr));
+    return SPECK_OK;
+}
+
+int speck_b200_push_slab_f64(speck_ctx *c, const speck_csr *S, uint64_t nnzBase, uint32_t rowBase, int last, uint32_t *dstRp,
+                             uint32_t *dstCi, double *dstV, float *deviceMs)
+{
+    return push_slab_impl<double>(c, S, nnzBase, rowBase, last, dstRp, dstCi, dstV, deviceMs);
+}
+
+int speck_b200_push_slab_f32(speck_ctx *c, const speck_csr *S, uint64_t nnzBase, uint32_t rowBase, int last, uint32_t *dstRp,
+                             uint32_t *dstCi, float *dstV, float *deviceMs)
+{
+    return push_slab_impl<float>(c, S, nnzBase, rowBase, last, dstRp, dstCi, dstV, deviceMs);
 }
 
 int speck_b200_sharded_slab(speck_shard_plan *p, int g, speck_csr *A_slab, speck_csr *C_slab)

@@ -135,6 +135,11 @@ void launch_publish(const LaunchCtx &lc, const Scalars *dSc, Scalars *hSc, volat
 void launch_row_cost(const LaunchCtx &lc, u32 rows, const u32 *aRp, u32 *rowOps, u32 wRow, u32 wEntry);
 void launch_find_cuts(const LaunchCtx &lc, const u64 *prefix, u32 rows, u32 parts, u32 *cuts, u64 *partProducts);
 void launch_offset_rows(const LaunchCtx &lc, const u32 *in, u32 n, u32 base, u32 *out);
+// one slab of C -> its place in the concatenated C (possibly peer memory): columns and values at nnzBase, row offsets
+// with nnzBase added at rowBase; 16-byte stores
+template <typename T>
+void launch_push_slab(const LaunchCtx &lc, const u32 *srcRp, const u32 *srcCi, const T *srcV, u32 rowsOut, u64 nnz,
+                      u64 nnzBase, u32 rowBase, u32 *dstRp, u32 *dstCi, T *dstV);
 
 // Rank map: one u16 per product of a mapped row, written by the symbolic phase at mapBase[row] + (index of the
 // product in the row's flat enumeration: A entries ascending, then B-row order):

@@ -589,6 +589,67 @@ void launch_offset_rows(const LaunchCtx &lc, const u32 *in, u32 n, u32 base, u32
 }
 
 // ------------------------------------------------------------------------------------------
+// Push of one slab of C into the concatenated C (one process per GPU: the destination is peer memory opened through
+// CUDA IPC, the stores travel over NVLink / NVSwitch; the gathering device pushes its own slab with the same kernel).
+// The transfer and the row_offsets fix-up are one kernel: every thread moves 16-byte pieces (destination-aligned, the
+// source is read element-wise when the two are not aligned alike), row offsets get the slab's nnz offset added on
+// the way.  Stores, not loads, cross the link: a store needs no round trip.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__device__ __forceinline__ void push_elems(E *__restrict__ dst, const E *__restrict__ src, u64 n, u64 gtid, u64 gsize)
+{
+    constexpr u32 V = 16 / sizeof(E);
+    u64 head = ((16u - (u32)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) / sizeof(E);
+    if (head > n) head = n;
+    for (u64 i = gtid; i < head; i += gsize) dst[i] = src[i];
+    const u64 body = (n - head) / V;
+    const E *s0 = src + head;
+    uint4 *d0 = reinterpret_cast<uint4 *>(dst + head);
+    if ((reinterpret_cast<uintptr_t>(s0) & 15u) == 0) {
+        const uint4 *sv = reinterpret_cast<const uint4 *>(s0);
+        u64 j = gtid;
+        for (; j + 3 * gsize < body; j += 4 * gsize) {   // four 16-byte pieces in flight per thread
+            const uint4 a = sv[j], b = sv[j + gsize], c = sv[j + 2 * gsize], d = sv[j + 3 * gsize];
+            d0[j] = a; d0[j + gsize] = b; d0[j + 2 * gsize] = c; d0[j + 3 * gsize] = d;
+        }
+        for (; j < body; j += gsize) d0[j] = sv[j];
+    } else {
+        for (u64 j = gtid; j < body; j += gsize) {
+            union { uint4 v; E e[V]; } t;
+#pragma unroll
+            for (u32 k = 0; k < V; ++k) t.e[k] = s0[j * V + k];
+            d0[j] = t.v;
+        }
+    }
+    for (u64 i = head + body * V + gtid; i < n; i += gsize) dst[i] = src[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_push_slab(const u32 *__restrict__ srcRp, const u32 *__restrict__ srcCi,
+                                                   const T *__restrict__ srcV, u32 rowsOut, u64 nnz, u32 nnzBase,
+                                                   u32 *__restrict__ dstRp, u32 *__restrict__ dstCi, T *__restrict__ dstV)
+{
+    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x, gsize = (u64)gridDim.x * blockDim.x;
+    for (u64 i = gtid; i < rowsOut; i += gsize) dstRp[i] = srcRp[i] + nnzBase;
+    push_elems<u32>(dstCi, srcCi, nnz, gtid, gsize);
+    push_elems<T>(dstV, srcV, nnz, gtid, gsize);
+}
+
+template <typename T>
+void launch_push_slab(const LaunchCtx &lc, const u32 *srcRp, const u32 *srcCi, const T *srcV, u32 rowsOut, u64 nnz,
+                      u64 nnzBase, u32 rowBase, u32 *dstRp, u32 *dstCi, T *dstV)
+{
+    if (rowsOut == 0 && nnz == 0) return;
+    k_push_slab<T><<<lc.smCount * 8, 256, 0, lc.stream>>>(srcRp, srcCi, srcV, rowsOut, nnz, (u32)nnzBase, dstRp + rowBase,
+                                                          dstCi + nnzBase, dstV + nnzBase);
+    ++*lc.launches;
+}
+template void launch_push_slab<double>(const LaunchCtx &, const u32 *, const u32 *, const double *, u32, u64, u64, u32, u32 *,
+                                       u32 *, double *);
+template void launch_push_slab<float>(const LaunchCtx &, const u32 *, const u32 *, const float *, u32, u64, u64, u32, u32 *,
+                                      u32 *, float *);
+
+// ------------------------------------------------------------------------------------------
 // Direct rows: A row with one entry -> C row = a_ik * B_k, already sorted.
 // (reference: directSpGEMMNumericImplementation, spECK_HashSpGEMM.cuh:543-569)
 // ------------------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ concatenation must be bit-identical in indices to the unsharded product and to t
 import numpy as np
 import pytest
 
-from speck_b200 import matrices as M
+from speck_b200 import api, matrices as M
 from speck_b200.matrices import HostCSR
 from speck_b200.sharding import concat_slabs
 from helpers import assert_csr_equal, gpu_multiply, oracle_multiply
@@ -128,3 +128,43 @@ def test_partition_rows_with_row_and_entry_costs(ctx):
     want = np.concatenate([[0], np.searchsorted(prefix, (np.arange(1, 4) * prefix[-1]) // 4, side="left"), [A.rows]])
     np.testing.assert_array_equal(cuts.astype(np.int64), want)
     assert [int(x) for x in cost] == [int(prefix[want[g + 1]] - prefix[want[g]]) for g in range(4)]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_push_slab_concatenates_slabs(ctx, dtype):
+    """speck_b200_push_slab_*: slabs of C pushed into the arrays of the concatenated C (here local memory; in the
+    one-process-per-GPU bench the same kernel stores into IPC-opened peer memory).  Cuts chosen so that the nnz offsets
+    are odd / even / multiples of 4 (16-byte store alignment of both arrays), two one-row slabs, one empty slab."""
+    import ctypes
+    A = M.rmat(12, 8, seed=31, dtype=dtype)
+    C = oracle_multiply(A.astype(np.float64), A.astype(np.float64))
+    C = HostCSR(C.rows, C.cols, C.row_offsets, C.col_ids, C.data.astype(dtype))
+    rp = C.row_offsets.astype(np.int64)
+    cuts = [0, 1, 2, 700, 700, 1501, 2222, C.rows]
+    # make sure the offsets cover every residue mod 4 somewhere
+    assert len({int(rp[c]) % 4 for c in cuts[1:-1]}) >= 3
+    d_rp = ctx._alloc((C.rows + 1) * 4)
+    d_ci = ctx._alloc(max(C.nnz, 1) * 4)
+    d_v = ctx._alloc(max(C.nnz, 1) * np.dtype(dtype).itemsize)
+    try:
+        for g in range(len(cuts) - 1):
+            r0, r1 = cuts[g], cuts[g + 1]
+            slab = C.row_slice(r0, r1)
+            last = g == len(cuts) - 2
+            if slab.nnz == 0 and r1 == r0:   # empty slab: nothing was multiplied, device arrays are null
+                d = api.DeviceCSR(ctx, dtype)
+                d.s.rows = 0
+                ms = ctx.push_slab(d, int(rp[r0]), r0, last, d_rp, d_ci, d_v)
+            else:
+                d = ctx.upload(slab)
+                ms = ctx.push_slab(d, int(rp[r0]), r0, last, d_rp, d_ci, d_v)
+                assert ms >= 0.0
+                d.free()
+        out = api.DeviceCSR.from_pointers(ctx, C.rows, C.cols, C.nnz, d_rp, d_ci, d_v, dtype)
+        got = ctx.download(out)
+        np.testing.assert_array_equal(got.row_offsets, C.row_offsets)
+        np.testing.assert_array_equal(got.col_ids, C.col_ids)
+        np.testing.assert_array_equal(got.data, C.data)
+    finally:
+        for p in (d_rp, d_ci, d_v):
+            ctx.lib.speck_b200_free(ctx.h, p)
