@@ -718,6 +718,7 @@ int push_slab_impl(speck_ctx *c, const speck_csr *S, uint64_t nnzBase, uint32_t 
     const u32 rowsOut = (u32)S->rows + (last ? 1u : 0u);
     u32 launches = 0;
     LaunchCtx lc{c->main, c->smCount, &launches};
+    finish_stage_times(c);   // two of the stage events are borrowed below: read the last multiply's times first
     cudaEventRecord(c->evStage[6], c->main);
     if (S->nnz && S->row_offsets) {
         launch_push_slab<T>(lc, S->row_offsets, S->col_ids, (const T *)S->data, rowsOut, S->nnz, nnzBase, rowBase, dstRp,
