@@ -259,6 +259,8 @@ int speck_b200_push_slab_f32(speck_ctx *ctx, const speck_csr *C_slab, uint64_t n
  *   "sym_mix"           N > 0: the sort kernels of the three largest lane-group classes run as capped grids (about N CTAs
  *                       per SM) next to the bitmap rank kernels instead of after them (measured slower; default 0)
  *   "seg_num", "hash_count"        experiments kept for the record (profiles/r2_notes.md), off by default
+ *   "rank_map_max_bytes"  upper bound of the rank-map workspace (-1 = no bound); a multiply whose map would be larger
+ *                       runs the self-contained numeric kernels instead (tests use it to force that fallback)
  *   "release_workspace" 1 frees the pooled workspace now. */
 int speck_b200_set_option(speck_ctx *ctx, const char *key, long long value);
 

@@ -156,3 +156,14 @@ def test_runspeck_binary_and_static_lib_exist():
     syms = subprocess.run(["nm", "-C", os.path.join(lib, "libspECKLib.a")], capture_output=True, text=True).stdout
     assert "spECK::MultiplyspECK<double, 4, 1024, 49152, 49152>" in syms
     assert "spECK::MultiplyspECK<float, 4, 1024, 49152, 49152>" in syms
+
+
+def test_every_library_option_is_documented_in_the_header():
+    """speck_b200_set_option keys (capi.cu) <-> the option list in include/speck_b200.h."""
+    import re
+    src = open(os.path.join(ROOT, "speck_b200", "csrc", "capi.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "speck_b200.h")).read()
+    keys = set(re.findall(r'strcmp\(key, "([a-z_]+)"\)', src))
+    assert len(keys) >= 20
+    missing = sorted(k for k in keys if f'"{k}"' not in hdr)
+    assert not missing, f"options without documentation in include/speck_b200.h: {missing}"
