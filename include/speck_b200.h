@@ -258,6 +258,8 @@ int speck_b200_push_slab_f32(speck_ctx *ctx, const speck_csr *C_slab, uint64_t n
  *                       register bitonic sort (measured slower; default 8 = off)
  *   "sym_mix"           N > 0: the sort kernels of the three largest lane-group classes run as capped grids (about N CTAs
  *                       per SM) next to the bitmap rank kernels instead of after them (measured slower; default 0)
+ *   "num_plan"          1: numeric phase of large multiplies (which use one stream): the one-CTA-per-SM kernels on a
+ *                       second stream next to the small shapes (experiment; default 0)
  *   "seg_num", "hash_count"        experiments kept for the record (profiles/r2_notes.md), off by default
  *   "rank_map_max_bytes"  upper bound of the rank-map workspace (-1 = no bound); a multiply whose map would be larger
  *                       runs the self-contained numeric kernels instead (tests use it to force that fallback)

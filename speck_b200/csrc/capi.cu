@@ -106,6 +106,8 @@ struct speck_ctx {
     int symMix = 0;           // symbolic phase: > 0 = the lane-group sort kernels of the 128 / 256 / 512-product classes
                               // (instruction-bound) run with about this many CTAs per SM, looping over their rows, next
                               // to the bitmap rank kernels (shared-memory-bound) instead of after them
+    int numPlan = 0;          // numeric phase of large multiplies (one stream): 1 = the one-CTA-per-SM kernels (bitmap rows,
+                              // 4097..16384-product classes) on a second stream next to the small shapes
     int bigSplit = 0;         // mapped numeric kernel of rows of 4097 .. 16384 products: 1..3 = several CTAs per row
                               // (map_split.cuh), 0 = one 1024-thread CTA per row
     int colDirect = 0;        // mapped numeric CTA kernels: 1..3 = the large shapes stage values only and write column ids
@@ -479,13 +481,14 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
 
     // ---- numeric
     const int numStreams = c->numStreams ? c->numStreams : (s1.products >= (1ull << 27) ? 1 : NSIDE);
+    const bool bigApart = c->numPlan == 1 && numStreams == 1;
     cudaEventRecord(c->evStage[4], c->main);
     fork_streams(c);
     sidx = 0;
     for (int loc = 0; loc < 2; ++loc) {
         const int bin = loc ? BIN_DENSE_LOCAL : BIN_DENSE;
         if (!s1.binCount[bin]) continue;
-        LaunchCtx ls{c->side[NSIDE - 1], c->smCount, &c->launches};
+        LaunchCtx ls{c->side[bigApart ? 1 : NSIDE - 1], c->smCount, &c->launches};
         launch_dense_numeric<T>(ls, loc != 0, perm + binStart[bin], s1.binCount[bin], &c->dSc->denseCounter[2 + loc],
                                 aRp, aCi, aV, bRp, bCi, bV, colsB, rowMin, rowMax, loc ? bitmapStore : nullptr, cRp, cCi, cV,
                                 denseSeq, rowOps);
@@ -498,7 +501,7 @@ int spgemm_impl(speck_ctx *c, const speck_csr *A, const speck_csr *B, speck_csr 
             const int b0 = rankGroupFirst[g], b1 = rankGroupFirst[g + 1];
             const u32 cnt = binStart[b1] - binStart[b0];
             if (!cnt) continue;
-            LaunchCtx ls{c->side[sidx++ % numStreams], c->smCount, &c->launches};
+            LaunchCtx ls{c->side[bigApart ? (g >= 3 ? 1 : 0) : sidx++ % numStreams], c->smCount, &c->launches};
             if (g == RANK_GROUPS - 1 && !rankMap) {
                 launch_dense_numeric<T>(ls, false, perm + binStart[b0], cnt, &c->dSc->denseCounter[5], aRp, aCi, aV, bRp, bCi,
                                         bV, colsB, rowMin, rowMax, nullptr, cRp, cCi, cV);
@@ -1376,6 +1379,11 @@ int speck_b200_set_option(speck_ctx *c, const char *key, long long value)
     if (!strcmp(key, "sym_mix")) {
         if (value < 0 || value > 16) return fail(SPECK_ERR_INVALID, "sym_mix must be in [0, 16]");
         c->symMix = (int)value;
+        return SPECK_OK;
+    }
+    if (!strcmp(key, "num_plan")) {
+        if (value < 0 || value > 1) return fail(SPECK_ERR_INVALID, "num_plan must be 0 or 1");
+        c->numPlan = (int)value;
         return SPECK_OK;
     }
     if (!strcmp(key, "big_split")) {
