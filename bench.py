@@ -338,11 +338,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the only NCCL traffic of this bench is point-to-point (slabs of C -> GPU 0, outside the multiply): with its
-        # default of a few channels per peer one send/recv pair moves ~200 GB/s of NVLink's 900
-        os.environ.setdefault("NCCL_NCHANNELS_PER_PEER", "32")
-        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
-        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
+        if args.concat != "push":
+            # NCCL send / recv path of the concatenation figure: with the default of a few channels per peer one
+            # send/recv pair moves ~200 GB/s of NVLink's 900 (the default path pushes with its own kernel instead)
+            os.environ.setdefault("NCCL_NCHANNELS_PER_PEER", "32")
+            os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+            os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = api.Context(local_rank)
