@@ -167,3 +167,19 @@ def test_every_library_option_is_documented_in_the_header():
     assert len(keys) >= 20
     missing = sorted(k for k in keys if f'"{k}"' not in hdr)
     assert not missing, f"options without documentation in include/speck_b200.h: {missing}"
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU oracle port on the arm's workload) runs without a GPU and prints the
+    contract's JSON line: same metric / unit as our arm, cpu_baseline describing the run, e2e equal to the value."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "rmat16",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "GFLOPS" and d["higher_is_better"] is True
+    assert d["metric"].startswith("SpGEMM GFLOPS") and d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
